@@ -1,0 +1,201 @@
+/*
+ * skeldiff_b200.h — C ABI of libskeldiff_sm100a.so
+ *
+ * B200-native (sm_100a) kernels for SkeletonDiffusion's nonisotropic latent-diffusion sampling
+ * path.  The reference has no FFI: its boundary is a set of Python classes.  Each
+ * entry point below names the reference method(s) it replaces (file:line under /root/reference).
+ * The Python classes in skeletondiffusion_b200/ keep the reference's names/signatures/state_dict
+ * keys and bind these symbols with ctypes.
+ *
+ * Conventions
+ *   - All pointers named *_dev are CUDA device pointers owned by the caller; the library never
+ *     allocates device memory, never synchronises the device, and launches only on `stream`
+ *     (a cudaStream_t passed as void*).  All calls are CUDA-graph capturable unless noted.
+ *   - Activations are row-major fp32 [B, N, C] ("sample-major": node rows of one sample are
+ *     contiguous).  A *view* (ptr, sample_stride, node_stride, rep) addresses row (b, n) at
+ *     ptr + (b / rep) * sample_stride + n * node_stride, so repeat_interleave'd conditioning and
+ *     time-sliced observations are read in place, never materialised.
+ *   - Every function returns 0 on success, non-zero on failure; sd_last_error() returns a
+ *     thread-local message.  Handles are re-entrant per stream; one handle set per device.
+ */
+#ifndef SKELDIFF_B200_H
+#define SKELDIFF_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SD_OK 0
+#define SD_ERR_INVALID 1
+#define SD_ERR_CUDA 2
+#define SD_ERR_UNSUPPORTED 3
+
+#define SD_MAX_NODES 64
+
+/* precision of the GEMM data path */
+#define SD_PREC_FP32 0      /* FFMA, fp32 operands and accumulation (parity gate <= 1e-4)            */
+#define SD_PREC_BF16 1      /* tcgen05 kind::f16, bf16 operands, fp32 accumulation in TMEM            */
+#define SD_PREC_BF16X3 2    /* tcgen05, operands split into 3 bf16 planes (fp32-grade products)       */
+
+#define SD_ACT_NONE 0
+#define SD_ACT_TANH 1
+#define SD_ACT_TANH_TANH 2   /* tanh(tanh(v)): encoder fc + z_activation (encoder.py:81, autoencoder.py:54) */
+
+typedef struct sd_glin sd_glin;           /* one StaticGraphLinear                                  */
+typedef struct sd_denoiser sd_denoiser;   /* Denoiser forward plan                                  */
+typedef struct sd_diffusion sd_diffusion; /* per-step nonisotropic tables                           */
+typedef struct sd_gru sd_gru;             /* one StaticGraphGRU cell                                */
+
+/* strided view of a [B, N, width] fp32 activation (see Conventions) */
+typedef struct sd_view {
+    float*  ptr;
+    int64_t sample_stride;
+    int64_t node_stride;
+    int32_t rep;      /* >=1: row b reads sample b / rep */
+    int32_t width;    /* channels addressed through this view */
+} sd_view;
+
+const char* sd_last_error(void);
+int         sd_version(void);
+/* 1 if the library carries sm_100a code and device `dev` is compute capability 10.x */
+int         sd_device_supported(int dev);
+
+/* ------------------------------------------------------------------ StaticGraphLinear ------
+ * replaces GraphLinear.forward / gmm   (src/core/network/layers/graph_structural.py:30-43, 7-8)
+ *   out[b,n,:] = sum_m G^[n,m] * ( x[b,m,:] @ W[type(m)]^T + bias[type(m)] )
+ * Host-side packing (skeletondiffusion_b200/plan.py) passes:
+ *   weight_dev    [n_types, out, in] fp32 (n_types == 1 when node_types is None)
+ *   bias_node_dev [N, out] = G^ @ bias[type]   (NULL when the layer has no bias)
+ *   g_dev         [N, N] row-L1-normalised G^ (NULL when G^ == I: the mix is skipped, exact)
+ */
+int  sd_glin_create(int num_nodes, const int32_t* node_types_host, int n_types, int in_features,
+                    int out_features, const float* weight_dev, const float* bias_node_dev,
+                    const float* g_dev, sd_glin** out);
+/* optional bf16 weight planes [planes][n_types, out, in] for the tcgen05 paths (planes = 1 or 3) */
+int  sd_glin_set_bf16(sd_glin* L, const uint16_t* weight_bf16_dev, int planes);
+void sd_glin_destroy(sd_glin* L);
+
+typedef struct sd_glin_args {
+    sd_view a0;                 /* first K segment (a0.width columns)                               */
+    sd_view a1;                 /* optional second K segment (ptr NULL if unused): concat-free cat  */
+    const float* row_scale_dev; /* optional [B*N]: multiplies row (b,m) of x@W^T before the mix    */
+    const float* scale_shift_dev; /* optional rows of [2*out]: v = v*(1+scale[o]) + shift[o]        */
+    const int32_t* ss_row_dev;  /* optional [B] row index into scale_shift (NULL -> ss_row)         */
+    int32_t ss_row;
+    int64_t ss_row_stride;      /* elements between scale_shift rows                                */
+    int32_t act;                /* SD_ACT_*                                                         */
+    sd_view residual;           /* optional (ptr NULL if unused), added after the activation        */
+    sd_view out;
+    float*  scratch_dev;        /* >= B*N*out floats, required iff the layer has a non-identity G^  */
+    int32_t batch;
+    int32_t precision;          /* SD_PREC_*                                                        */
+} sd_glin_args;
+
+int sd_glin_forward(const sd_glin* L, const sd_glin_args* args, void* stream);
+
+/* ------------------------------------------------------------------ node attention ---------
+ * replaces Attention.forward's softmax(q k^T) v over nodes (layers/attention.py:125-135)
+ *   qkv_dev [B, N, 3*heads*dim_head] (q | k | v, head-major inside each), out [B, N, heads*dim_head]
+ */
+int sd_node_attention(const float* qkv_dev, float* out_dev, int batch, int num_nodes, int heads,
+                      int dim_head, void* stream);
+
+/* RMSNorm row factor (layers/attention.py:36): inv_norm[r] = 1 / max(||x[r,:]||_2, 1e-12) */
+int sd_row_inv_norm(const float* x_dev, float* inv_norm_dev, int64_t rows, int width, void* stream);
+
+/* ------------------------------------------------------------------ time conditioning ------
+ * replaces SinusoidalPosEmb -> Linear -> GELU -> Linear (nn/generator.py:47-55) and the
+ * ResnetBlock heads Tanh -> Linear (layers/attention.py:81-84) for `n_rows` distinct time values.
+ *   table_dev [n_rows, n_heads, 2*C];  workspace >= n_rows * (C + 2*time_dim) floats
+ */
+int sd_time_table(const float* times_dev, int n_rows, int C, float theta, int time_dim,
+                  const float* w1_dev, const float* b1_dev, const float* w3_dev, const float* b3_dev,
+                  const float* const* head_w_dev_host, const float* const* head_b_dev_host,
+                  int n_heads, float* table_dev, float* workspace_dev, void* stream);
+
+/* ------------------------------------------------------------------ Denoiser ---------------
+ * replaces Denoiser.forward (nn/generator.py:86-107) incl. ResnetBlock / Block / PreNorm /
+ * Attention / Residual (layers/attention.py:11-136).
+ * slots: 0 init_lin; for pair i in [0, 2*depth): 1+4i block1.proj, 2+4i block2.proj, 3+4i to_qkv,
+ *        4+4i to_out (pair 2*depth-1 has no attention); then final_res_block.block1, .block2,
+ *        .res_linear, final_glin at 1+8*depth + {0,1,2,3}.
+ * to_qkv weights must be pre-multiplied by norm.g * sqrt(C) (RMSNorm gain folded at pack time).
+ */
+int  sd_denoiser_create(int num_nodes, int dim, int cond_dim, int out_dim, int depth, int heads,
+                        int dim_head, sd_denoiser** out);
+int  sd_denoiser_set_layer(sd_denoiser* d, int slot, const sd_glin* layer);
+/* scale/shift table from sd_time_table: [n_rows, 2*depth+1, 2*C] */
+int  sd_denoiser_set_time_table(sd_denoiser* d, const float* table_dev, int n_rows);
+void sd_denoiser_destroy(sd_denoiser* d);
+size_t sd_denoiser_workspace_bytes(const sd_denoiser* d, int batch, int precision);
+/* t_rows_dev: optional [B] per-sample row of the time table; NULL -> all samples use t_row */
+int  sd_denoiser_forward(const sd_denoiser* d, const sd_view* x, const sd_view* x_cond,
+                         const int32_t* t_rows_dev, int t_row, float* out_dev, int batch,
+                         void* workspace_dev, int precision, void* stream);
+
+/* ------------------------------------------------------------------ reverse diffusion ------
+ * replaces p_sample / p_mean_variance / q_posterior / p_combine_mean_var_noise
+ * (diffusion/base.py:314-341, diffusion/nonisotropic.py:196-210):
+ *   x_{t-1} = C1[t] clamp(x0) + C2[t] x_t + S[t] eps,  S[t] = U diag(exp(0.5 logLambda_post[t]))
+ * tables [T, N, N] fp32 on device (posterior_mean_coef1_x0, posterior_mean_coef2_xt, S).
+ */
+int  sd_diffusion_create(int num_nodes, int latent_dim, int timesteps, const float* c1_dev,
+                         const float* c2_dev, const float* s_dev, const float* c1_host,
+                         const float* c2_host, const float* s_host, sd_diffusion** out);
+void sd_diffusion_destroy(sd_diffusion* d);
+/* eps_dev may be NULL (t == 0: no noise).  mean_out_dev optional.  eps addressed as a view so
+ * sampling_noise[:, T-1-t] is read in place. */
+int  sd_reverse_step(const sd_diffusion* d, const float* x_t_dev, const float* x0_dev,
+                     const sd_view* eps, float* x_out_dev, float* mean_out_dev, int t, int batch,
+                     int clip_denoised, void* stream);
+/* forward process q_sample (nonisotropic.py:152-159): x = sqrt_ac[t_b] x0 + M[t_b] eps, M = U sqrt(Lambda_bar_t) */
+int  sd_q_sample(const float* x0_dev, const float* eps_dev, const int32_t* t_dev,
+                 const float* sqrt_ac_dev, const float* m_dev, float* out_dev, int batch,
+                 int num_nodes, int latent_dim, void* stream);
+/* Mahalanobis l1 loss (nonisotropic.py:180-190 + base.py:298): loss[b] = mean |S[t_b] (out - x0)| */
+int  sd_mahalanobis_loss(const float* out_dev, const float* x0_dev, const int32_t* t_dev,
+                         const float* s_dev, float* loss_dev, int batch, int num_nodes,
+                         int latent_dim, void* stream);
+
+/* whole p_sample_loop (diffusion/base.py:343-390): x_dev holds x_T on entry and x_0 on exit.
+ * sampling_noise_dev [B, T-1, N, D] (required; throughput mode fills it with sd_fill_normal).
+ * means_out_dev optional [B, T-1, N, D] (return_sampling_noise=True). */
+size_t sd_sample_workspace_bytes(const sd_diffusion* df, const sd_denoiser* dn, int batch, int precision);
+int  sd_sample_loop(const sd_diffusion* df, const sd_denoiser* dn, float* x_dev, const sd_view* x_cond,
+                    const float* sampling_noise_dev, float* means_out_dev, int batch,
+                    int clip_denoised, void* workspace_dev, int precision, void* stream);
+
+/* counter-based N(0,1) generator (Philox4x32-10 + Box-Muller); replaces torch.randn at base.py:156-158 */
+int  sd_fill_normal(float* out_dev, int64_t count, uint64_t seed, uint64_t offset, void* stream);
+
+/* ------------------------------------------------------------------ graph GRU / autoencoder -
+ * replaces StaticGraphGRUCell_.forward (layers/recurrent.py:321-366) and the loops of
+ * Encoder.forward (nn/encoder.py:77-82) / Decoder.forward (nn/decoder.py:85-104).
+ * gx_seq_dev: [steps, N, N] the data-independent sequence gx_i (NULL when every gx_i == I);
+ * bias_*_seq_dev: [steps, N, 3H] = gx_i @ bias[type].
+ */
+int  sd_gru_create(int num_nodes, const int32_t* node_types_host, int n_types, int input_size,
+                   int hidden_size, const float* w_ih_dev, const float* w_hh_dev,
+                   const float* bias_ih_seq_dev, const float* bias_hh_seq_dev,
+                   const float* gx_seq_dev, int steps, sd_gru** out);
+void sd_gru_destroy(sd_gru* g);
+size_t sd_encode_workspace_bytes(int windows, int obs_len, int num_nodes, int hidden, int layers);
+/* obs_dev [W, T, N, F] -> z_dev [W, N, latent] = final_act(fc(h_T)); final_act = SD_ACT_TANH_TANH for
+ * get_past_embedding with encoder_act = z_activation = tanh (encoder.py:81, autoencoder.py:51-55) */
+int  sd_encode(const sd_glin* initial_hidden, sd_gru* const* layers_host, int n_layers, const sd_glin* fc,
+               const float* obs_dev, int windows, int obs_len, int feat, float* z_dev, int final_act,
+               void* workspace_dev, int precision, void* stream);
+size_t sd_decode_workspace_bytes(int batch, int num_nodes, int hidden);
+/* x_last2 view: rows of obs[:, -2] (ptr) and obs[:, -1] (ptr + frame_stride); latent [B,N,L];
+ * out_dev [B, ph, N, F]  (autoencoder.py:66-73, decoder.py:61-104) */
+int  sd_decode(const sd_glin* initial_hidden, const sd_gru* cell, const sd_glin* fc,
+               const sd_view* x_prev, const sd_view* x_last, const float* latent_dev, int batch,
+               int ph, int feat, float* out_dev, void* workspace_dev, int precision, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKELDIFF_B200_H */

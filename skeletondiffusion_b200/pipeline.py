@@ -1,0 +1,107 @@
+"""Caller-side glue of the sampling path with the reference's signatures.
+
+Reference: get_diffusion_latent_codes / decode_latent_pred / get_prediction
+(src/eval_prepare_model.py:89-121) and DiffusionManager (src/core/diffusion_manager.py:8-45).
+The reference materialises `obs` and `z_past` num_samples times with repeat_interleave; here
+the kernels read the per-window rows in place (sd_view.rep), so nothing is replicated.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, Optional, Tuple
+
+import torch
+
+from .autoencoder import AutoEncoder
+from .diffusion import NonisotropicGaussianDiffusion, get_cov_from_corr
+from .network import Denoiser
+
+__all__ = ["DiffusionManager", "get_diffusion_latent_codes", "decode_latent_pred", "get_prediction",
+           "shard_windows", "build_models"]
+
+
+class DiffusionManager:
+    """Factory with the reference's keyword surface (diffusion_manager.py:8-45)."""
+
+    def __init__(self, diffusion_type: str = "IsotropicGaussianDiffusion", skeleton=None, covariance_matrix_type: str = "adjacency",
+                 reachability_matrix_degree_factor=0.5, reachability_matrix_stop_at=0, if_sigma_n_scale=True,
+                 sigma_n_scale="spectral", if_run_as_isotropic=False, **kwargs):
+        model = self.get_network(**kwargs)
+        self.diffusion_type = diffusion_type
+        if diffusion_type != "NonisotropicGaussianDiffusion":
+            raise NotImplementedError("IsotropicGaussianDiffusion is the reference's ablation class (SURVEY §2 row 4: out of scope); "
+                                      "use NonisotropicGaussianDiffusion with if_run_as_isotropic=True")
+        if covariance_matrix_type == "adjacency":
+            corr = skeleton.adj_matrix
+        elif covariance_matrix_type == "reachability":
+            corr = skeleton.reachability_matrix(factor=reachability_matrix_degree_factor, stop_at=reachability_matrix_stop_at)
+        else:
+            raise AssertionError("Not implemented")
+        sigma, lam, u = get_cov_from_corr(correlation_matrix=corr, if_sigma_n_scale=if_sigma_n_scale, sigma_n_scale=sigma_n_scale,
+                                          if_run_as_isotropic=if_run_as_isotropic, **kwargs)
+        self.diffusion = NonisotropicGaussianDiffusion(Sigma_N=sigma, Lambda_N=lam, U=u, model=model, **kwargs)
+
+    def get_diffusion(self):
+        return self.diffusion
+
+    def get_network(self, num_nodes, diffusion_conditioning=False, latent_size=96, node_types: torch.Tensor = None,
+                    diffusion_arch: Dict[str, Any] = None, **kwargs):
+        cond_dim = latent_size if diffusion_conditioning else 0
+        arch = dict(diffusion_arch or {})
+        arch.pop("arch", None)
+        return Denoiser(dim=latent_size, cond_dim=cond_dim, out_dim=latent_size, channels=num_nodes, num_nodes=num_nodes,
+                        node_types=node_types, **arch)
+
+
+def get_diffusion_latent_codes(obs, model, num_samples=50, **kwargs):
+    autoencoder, diffusion = model
+    bs = obs.shape[0]
+    sampler_kwargs = kwargs.get("sampler_kwargs", {})
+    past_embedding = autoencoder.get_past_embedding(obs)
+    if kwargs.get("diffusion_conditioning", True):
+        # x_cond has bs rows, the batch bs*num_samples: rows are repeat_interleave'd in place (base.py:246-248)
+        latent_pred, _ = diffusion.sample(batch_size=bs * num_samples, x_cond=past_embedding, **sampler_kwargs)
+    else:
+        latent_pred, _ = diffusion.sample(batch_size=bs * num_samples, **sampler_kwargs)
+    return latent_pred, past_embedding
+
+
+def decode_latent_pred(obs, latent_pred, z_past, model, num_samples=50, pred_length=100, **kwargs):
+    autoencoder, _ = model
+    bs, _, j, f = obs.shape
+    pred = autoencoder.decode(obs, latent_pred, z_past, ph=pred_length)       # obs rows shared by the samples of a window
+    return pred.view(bs, num_samples, pred_length, j, f)
+
+
+def get_prediction(obs, model, num_samples=50, pred_length=100, **kwargs):
+    """obs [W, T_obs, N, 3] -> predictions [W, num_samples, pred_length, N, 3] (eval_prepare_model.py:118-121)."""
+    lat_pred, z_past = get_diffusion_latent_codes(obs, model, num_samples=num_samples, **kwargs)
+    return decode_latent_pred(obs, lat_pred, z_past, model, num_samples=num_samples, pred_length=pred_length, **kwargs)
+
+
+def shard_windows(num_windows: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous window range [lo, hi) of `rank`; all samples of a window stay on one GPU so APD/ADE/FDE
+    (which reduce over the samples of a window) need no exchange."""
+    base, rem = divmod(num_windows, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def build_models(skeleton, device, diffusion_timesteps: int = 10, depth: int = 4, attn_heads: int = 8, attn_dim_head: int = 32,
+                 latent_size: int = 96, if_run_as_isotropic: bool = False, precision: str = "fp32", seed: Optional[int] = 0):
+    """Dataset-config models (configs/config_train_diffusion/model/skeleton_diffusion.yaml:49-57,
+    config_train_autoencoder/model/autoencoder.yaml) with reference-style random initialisation."""
+    if seed is not None:
+        torch.manual_seed(seed)
+    nt = skeleton.nodes_type_id
+    ae = AutoEncoder(num_nodes=skeleton.num_nodes, encoder_hidden_size=96, decoder_hidden_size=96, latent_size=latent_size,
+                     node_types=nt, input_size=3, z_activation="tanh", enc_num_layers=skeleton.enc_num_layers,
+                     recurrent_arch_enc="StaticGraphGRU", recurrent_arch_decoder="StaticGraphGRU", output_size=3,
+                     if_consider_hip=False)
+    mgr = DiffusionManager(diffusion_type="NonisotropicGaussianDiffusion", skeleton=skeleton, covariance_matrix_type="adjacency",
+                           num_nodes=skeleton.num_nodes, node_types=nt, diffusion_conditioning=True, latent_size=latent_size,
+                           diffusion_timesteps=diffusion_timesteps, diffusion_objective="pred_x0", beta_schedule="cosine",
+                           if_run_as_isotropic=if_run_as_isotropic, precision=precision,
+                           diffusion_arch=dict(depth=depth, attn_heads=attn_heads, attn_dim_head=attn_dim_head, use_attention=True,
+                                               self_condition=False, norm_type="none", learn_influence=True))
+    diffusion = mgr.get_diffusion()
+    return ae.to(device).eval(), diffusion.to(device).eval()

@@ -1,0 +1,70 @@
+"""CPU: the oracle restatement (oracle/skeldiff_oracle.py) against golden vectors produced by the
+reference's own classes (tests/golden/make_golden.py).  This is what pins the oracle."""
+import pytest
+import torch
+
+from oracle import skeldiff_oracle as oc
+from tests import _golden as G
+
+TOL = 2e-6   # fp32 re-association only: both sides are fp32 CPU PyTorch
+
+
+@pytest.mark.parametrize("name", G.README_CASES)
+def test_readme_case(name):
+    case = G.load_npz(name)
+    diff, sd, corr = G.readme_models(case)
+    tabs = G.tables_of(case)
+    # covariance + tables
+    sigma, lam, u = oc.cov_from_corr(corr)
+    assert torch.allclose(sigma, tabs["Sigma_N"], atol=1e-6) and torch.allclose(lam, tabs["Lambda_N"], atol=1e-6)
+    mine = oc.diffusion_tables(tabs["Lambda_N"], tabs["U"], 10)
+    for k in ("betas", "alphas_cumprod", "posterior_mean_coef1_x0", "posterior_mean_coef2_xt", "Lambda_posterior",
+              "Lambda_posterior_log_variance_clipped", "Umm_sqrt_Lambda_bar_t", "mahalanobis_S_sqrt_recip", "loss_weight"):
+        assert torch.allclose(mine[k], tabs[k], atol=1e-6, rtol=1e-5), k
+    out = oc.denoiser_forward(sd, G.README_CFG, case["x_probe"], case["t_probe"], None, prefix="model.")
+    assert G.rel_err(out, case["den_out"]) < TOL
+    lat, means = oc.sample(sd, G.README_CFG, tabs, tabs["U"], None, case["start_noise"], case["sampling_noise"], return_means=True)
+    assert G.rel_err(means, case["mean_t"]) < 5 * TOL
+    assert G.rel_err(lat, case["latents"]) < 5 * TOL
+
+
+@pytest.mark.parametrize("name", G.DATASET_CASES)
+def test_dataset_case(name):
+    case = G.load_npz(name)
+    spec, ae, diff, ae_sd, diff_sd = G.dataset_models(case)
+    cfg = G.dataset_cfg(spec)
+    tabs = G.tables_of(case)
+    S = int(case["samples"])
+    mine = oc.diffusion_tables(tabs["Lambda_N"], tabs["U"], 10)
+    for k in ("posterior_mean_coef1_x0", "posterior_mean_coef2_xt", "Lambda_posterior_log_variance_clipped"):
+        assert torch.allclose(mine[k], tabs[k], atol=1e-6, rtol=1e-5), k
+    z = oc.encode(ae_sd, cfg, case["obs"])
+    assert G.rel_err(z, case["z_past"]) < TOL
+    zc = case["z_past"].repeat_interleave(S, 0)
+    out = oc.denoiser_forward(diff_sd, cfg, case["x_probe"], case["t_probe"], zc, prefix="model.")
+    assert G.rel_err(out, case["den_out"]) < 5 * TOL
+    lat, means = oc.sample(diff_sd, cfg, tabs, tabs["U"], zc, case["start_noise"], case["sampling_noise"], return_means=True)
+    assert G.rel_err(means, case["mean_t"]) < 2e-5
+    assert G.rel_err(lat, case["latents"]) < 2e-5
+    pred = oc.decode(ae_sd, cfg, case["obs"][:, -2:].repeat_interleave(S, 0), case["latents"], int(case["ph"]))
+    assert G.rel_err(pred.view(case["pred"].shape), case["pred"]) < 2e-5
+    # training-loss entry point
+    xq = oc.q_sample(tabs, case["x_start"], case["t_loss"], case["noise_loss"])
+    assert G.rel_err(xq, case["q_sample"]) < TOL
+    loss, lw, mout = oc.p_losses(diff_sd, cfg, tabs, case["x_start"], case["t_loss"], case["noise_loss"], zc)
+    assert G.rel_err(mout, case["loss_model_out"]) < 5 * TOL
+    assert G.rel_err(loss, case["loss"]) < 1e-5 and torch.allclose(lw.reshape(-1), case["loss_weight"].reshape(-1))
+    # metrics
+    pm, tm = spec.transform_to_metric_space(case["pred"]), spec.transform_to_metric_space(case["target"])
+    assert torch.allclose(oc.ade(tm, pm), case["ade"], atol=1e-6)
+    assert torch.allclose(oc.fde(tm, pm), case["fde"], atol=1e-6)
+    assert torch.allclose(oc.apd(pm), case["apd"], atol=1e-5)
+
+
+def test_isotropic_tables_are_diagonal():
+    case = G.load_npz("amass_perturbed_iso")
+    tabs = G.tables_of(case)
+    eye = torch.eye(21)
+    assert torch.equal(tabs["U"], eye)
+    off = tabs["posterior_mean_coef1_x0"] * (1 - eye)
+    assert float(off.abs().max()) == 0.0
