@@ -60,6 +60,8 @@ typedef struct sd_view {
 
 const char* sd_last_error(void);
 int         sd_version(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches evidence) */
+uint64_t    sd_launch_count(void);
 /* 1 if the library carries sm_100a code and device `dev` is compute capability 10.x */
 int         sd_device_supported(int dev);
 

@@ -12,7 +12,7 @@ from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent / "csrc"
 LIB = CSRC / "libskeldiff_sm100a.so"
-SOURCES = ["sd_api.cu", "sd_glin_fp32.cu", "sd_elem_fp32.cu", "sd_glin_tc.cu"]
+SOURCES = ["sd_api.cu", "sd_glin_fp32.cu", "sd_elem_fp32.cu", "sd_attention.cu", "sd_glin_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 
@@ -40,17 +40,21 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and LIB.exists() and stamp_file.exists() and stamp_file.read_text() == stamp:
         return LIB
     nvcc = _nvcc()
-    objs = []
-    log = []
-    for src in SOURCES:
+    from concurrent.futures import ThreadPoolExecutor
+
+    def compile_one(src):
         obj = CSRC / (Path(src).stem + ".o")
         cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
-        log.append(r.stderr)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
-        objs.append(str(obj))
-    cmd = [nvcc, "-shared", "-o", str(LIB), *objs, "-lcudart", "-lcuda"]
+        return str(obj), r.stderr
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as ex:
+        results = list(ex.map(compile_one, SOURCES))
+    objs = [o for o, _ in results]
+    log = [l for _, l in results]
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(LIB), *objs, "-lcudart", "-lcuda"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

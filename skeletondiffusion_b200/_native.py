@@ -42,6 +42,7 @@ _P, _I, _I64, _U64, _F, _SZ = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_fl
 SIGNATURES = {
     "sd_last_error": (C.c_char_p, []),
     "sd_version": (_I, []),
+    "sd_launch_count": (_U64, []),
     "sd_device_supported": (_I, [_I]),
     "sd_glin_create": (_I, [_I, _P, _I, _I, _I, _P, _P, _P, C.POINTER(_P)]),
     "sd_glin_set_bf16": (_I, [_P, _P, _I]),

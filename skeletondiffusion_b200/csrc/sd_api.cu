@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <atomic>
 
 namespace sd {
 
@@ -22,6 +23,9 @@ int check_cuda(cudaError_t e, const char* what) {
     set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
     return 1;
 }
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 static inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
@@ -58,6 +62,7 @@ extern "C" {
 
 const char* sd_last_error(void) { return g_err; }
 int sd_version(void) { return 100; }
+uint64_t sd_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int sd_device_supported(int dev) {
     cudaDeviceProp p;

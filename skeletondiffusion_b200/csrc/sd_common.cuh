@@ -68,8 +68,9 @@ __device__ __forceinline__ float epilogue_apply(const Epilogue& e, int b, int n,
 
 void set_error(const char* fmt, ...);
 int  check_cuda(cudaError_t e, const char* what);
+void count_launch();   // every kernel launch of the library is counted (sd_launch_count)
 
 }  // namespace sd
 
 #define SD_CUDA_OK(expr) do { if (sd::check_cuda((expr), #expr)) return SD_ERR_CUDA; } while (0)
-#define SD_LAUNCH_OK(what) do { if (sd::check_cuda(cudaGetLastError(), what)) return SD_ERR_CUDA; } while (0)
+#define SD_LAUNCH_OK(what) do { sd::count_launch(); if (sd::check_cuda(cudaGetLastError(), what)) return SD_ERR_CUDA; } while (0)

@@ -1,0 +1,242 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against
+(i) golden vectors produced by the reference's own classes and (ii) the CPU oracle on seeded inputs.
+fp32 gate: max|a-b| / max|b| <= 1e-4 (BASELINE.json north_star)."""
+import ctypes as C
+
+import pytest
+import torch
+
+from oracle import skeldiff_oracle as oc
+from tests import _golden as G
+
+pytestmark = pytest.mark.gpu
+FP32_TOL = 1e-4
+
+
+def _native():
+    from skeletondiffusion_b200 import _native as nv
+    return nv
+
+
+# ------------------------------------------------------------------------------------------------
+# single operators against the oracle
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("typed,learn,bias,kin,kout,batch", [
+    (True, True, True, 192, 192, 5), (True, True, False, 192, 768, 130), (False, False, True, 96, 96, 4),
+    (True, True, True, 99, 96, 33), (True, True, True, 96, 3, 257), (True, False, True, 3, 96, 7),
+])
+def test_graph_linear_vs_oracle(cuda_device, typed, learn, bias, kin, kout, batch):
+    import skeletondiffusion_b200 as sdb
+    from skeletondiffusion_b200.testing import synth_state_dict
+    spec = sdb.get_skeleton("amass")
+    N = spec.num_nodes
+    nt = spec.nodes_type_id if typed else None
+    layer = sdb.StaticGraphLinear(kin, kout, bias=bias, num_nodes=N, node_types=nt, learn_influence=learn)
+    sd = synth_state_dict(layer.state_dict(), seed=5, mode="perturbed", gain=1.5)
+    layer.load_state_dict(sd)
+    x = torch.randn(batch, N, kin, generator=torch.Generator().manual_seed(1))
+    ref = oc.graph_linear({k: v for k, v in sd.items()}, "", x, nt, learn)
+    out = layer.to(cuda_device)(x.to(cuda_device))
+    assert G.rel_err(out.cpu(), ref) < FP32_TOL
+
+
+def test_graph_linear_identity_path_and_epilogue(cuda_device):
+    """G == I (fused epilogue, no scratch) with two K segments, in-place repeat, scale/shift, tanh, residual."""
+    import skeletondiffusion_b200 as sdb
+    from skeletondiffusion_b200 import _native as nv
+    from skeletondiffusion_b200.testing import synth_state_dict
+    spec = sdb.get_skeleton("h36m")
+    N, nt = spec.num_nodes, spec.nodes_type_id
+    layer = sdb.StaticGraphLinear(192, 192, bias=True, num_nodes=N, node_types=nt, learn_influence=True)
+    sd = synth_state_dict(layer.state_dict(), seed=9, mode="perturbed", gain=1.5)
+    sd["G"] = torch.eye(N)
+    layer.load_state_dict(sd)
+    g = torch.Generator().manual_seed(2)
+    W, S = 3, 5
+    cond = torch.randn(W, N, 96, generator=g)
+    x = torch.randn(W * S, N, 96, generator=g)
+    ss = torch.randn(4, 2 * 192, generator=g) * 0.3
+    rows = torch.tensor([i % 4 for i in range(W * S)], dtype=torch.int32)
+    res = torch.randn(W * S, N, 192, generator=g)
+    xin = torch.cat([cond.repeat_interleave(S, 0), x], -1)
+    y = oc.graph_linear(sd, "", xin, nt, True)
+    scale, shift = ss[rows.long()][:, None, :192], ss[rows.long()][:, None, 192:]
+    ref = torch.tanh(y * (scale + 1) + shift) + res
+    plan = layer.to(cuda_device).plan()
+    assert plan.identity
+    d = cuda_device
+    out = plan.forward(cond.to(d), x2=x.to(d), scale_shift=ss.to(d), ss_rows=rows.to(d), act=nv.ACT_TANH, residual=res.to(d), rep=S)
+    assert G.rel_err(out.cpu(), ref) < FP32_TOL
+
+
+@pytest.mark.parametrize("N,heads,dh", [(21, 8, 32), (16, 4, 32), (51, 8, 32), (17, 2, 16)])
+def test_node_attention_vs_oracle(cuda_device, N, heads, dh):
+    nv = _native()
+    g = torch.Generator().manual_seed(3)
+    B = 9
+    qkv = torch.randn(B, N, 3 * heads * dh, generator=g)
+    q, k, v = [t.reshape(B, N, heads, dh).permute(0, 2, 1, 3) for t in qkv.chunk(3, -1)]
+    attn = torch.einsum("bhnc,bhjc->bhnj", q * dh ** -0.5, k).softmax(-1)
+    ref = torch.einsum("bhnj,bhjd->bhnd", attn, v).permute(0, 2, 1, 3).reshape(B, N, heads * dh)
+    qd = qkv.to(cuda_device)
+    out = torch.empty(B, N, heads * dh, device=cuda_device)
+    nv.check(nv.load().sd_node_attention(qd.data_ptr(), out.data_ptr(), B, N, heads, dh, nv.stream_ptr(cuda_device)), "attn")
+    assert G.rel_err(out.cpu(), ref) < FP32_TOL
+
+
+@pytest.mark.parametrize("N,iso", [(21, False), (16, False), (17, False), (19, False), (21, True)])
+def test_reverse_step_vs_oracle(cuda_device, N, iso):
+    """Templated (16/17/21), generic (19) and diagonal (U = I) variants; t = 0 must equal clamp(x0)."""
+    import skeletondiffusion_b200 as sdb
+    g = torch.Generator().manual_seed(4)
+    rand = (torch.rand(N, N, generator=g) >= 0.5).float()
+    corr = (rand + rand.T) // 2
+    sigma, lam, u = sdb.get_cov_from_corr(corr, if_run_as_isotropic=iso)
+    tab = oc.diffusion_tables(lam, u, 10)
+    model = sdb.Denoiser(dim=96, cond_dim=0, out_dim=96, channels=N, num_nodes=N)
+    diff = sdb.NonisotropicGaussianDiffusion(Sigma_N=sigma, Lambda_N=lam, U=u, model=model).to(cuda_device)
+    B = 37
+    x_t, x0, eps = (torch.randn(B, N, 96, generator=g) for _ in range(3))
+    x0 = x0 * 1.5
+    for t in (9, 4, 1, 0):
+        ref, ref_mean = oc.reverse_step(tab, u, x_t, x0, t, eps if t > 0 else None)
+        out, mean = diff._reverse_step(x_t.to(cuda_device), x0.to(cuda_device), eps.to(cuda_device) if t > 0 else None, t, True, want_mean=True)
+        assert G.rel_err(out.cpu(), ref) < FP32_TOL and G.rel_err(mean.cpu(), ref_mean) < FP32_TOL
+        if t == 0:
+            assert G.rel_err(out.cpu(), x0.clamp(-1, 1)) < 1e-5
+
+
+def test_fill_normal_statistics(cuda_device):
+    nv = _native()
+    n = 1 << 22
+    a = torch.empty(n, device=cuda_device)
+    b = torch.empty(n, device=cuda_device)
+    nv.check(nv.load().sd_fill_normal(a.data_ptr(), n, 123, 0, nv.stream_ptr(cuda_device)), "fill")
+    nv.check(nv.load().sd_fill_normal(b.data_ptr(), n // 2, 123, n // 8, nv.stream_ptr(cuda_device)), "fill")
+    assert abs(float(a.mean())) < 3e-3 and abs(float(a.std()) - 1) < 3e-3
+    assert abs(float((a ** 4).mean()) - 3.0) < 0.05
+    assert torch.equal(a[n // 2:], b[:n // 2])          # counter-based: a shard reproduces its slice of the stream
+
+
+# ------------------------------------------------------------------------------------------------
+# composites against the reference's golden vectors
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", G.README_CASES)
+def test_readme_sampling_golden(cuda_device, name):
+    case = G.load_npz(name)
+    diff, sd, _ = G.readme_models(case, device=cuda_device)
+    d = cuda_device
+    out = diff.model(case["x_probe"].to(d), case["t_probe"].to(d))
+    assert G.rel_err(out.cpu(), case["den_out"]) < FP32_TOL
+    lat, (n0, noise_t, mean_t) = diff.sample(batch_size=4, start_noise=case["start_noise"].to(d),
+                                              sampling_noise=case["sampling_noise"].to(d), return_sampling_noise=True)
+    assert torch.equal(n0.cpu(), case["start_noise"])
+    assert G.rel_err(mean_t.cpu(), case["mean_t"]) < FP32_TOL
+    assert G.rel_err(lat.cpu(), case["latents"]) < FP32_TOL
+
+
+@pytest.mark.parametrize("name", G.DATASET_CASES)
+def test_dataset_pipeline_golden(cuda_device, name):
+    import skeletondiffusion_b200 as sdb
+    case = G.load_npz(name)
+    spec, ae, diff, ae_sd, diff_sd = G.dataset_models(case, device=cuda_device)
+    d = cuda_device
+    S, W, ph = int(case["samples"]), int(case["windows"]), int(case["ph"])
+    obs = case["obs"].to(d)
+    # (a9) encode
+    z = ae.get_past_embedding(obs)
+    assert G.rel_err(z.cpu(), case["z_past"]) < FP32_TOL
+    # (a5) one Denoiser forward with per-sample times and in-place repeated conditioning
+    out = diff.model(case["x_probe"].to(d), case["t_probe"].to(d), None, case["z_past"].to(d))
+    assert G.rel_err(out.cpu(), case["den_out"]) < FP32_TOL
+    # (a3/a4) whole reverse process with injected noise, per-step posterior means
+    lat, (_, _, mean_t) = diff.sample(batch_size=W * S, x_cond=case["z_past"].to(d), start_noise=case["start_noise"].to(d),
+                                      sampling_noise=case["sampling_noise"].to(d), return_sampling_noise=True)
+    assert G.rel_err(mean_t.cpu(), case["mean_t"]) < FP32_TOL
+    assert G.rel_err(lat.cpu(), case["latents"]) < FP32_TOL
+    # (a10) decode from the reference's latents
+    pred = ae.decode(obs, case["latents"].to(d), None, ph=ph)
+    assert G.rel_err(pred.cpu().view(case["pred"].shape), case["pred"]) < FP32_TOL
+    # (a12) the caller: get_prediction end to end, then ADE/FDE/APD to the printed precision (4 decimals, eval.py:109)
+    pred2 = sdb.get_prediction(obs, (ae, diff), num_samples=S, pred_length=ph, diffusion_conditioning=True,
+                               sampler_kwargs=dict(start_noise=case["start_noise"].to(d), sampling_noise=case["sampling_noise"].to(d)))
+    assert tuple(pred2.shape) == tuple(case["pred"].shape)
+    assert G.rel_err(pred2.cpu(), case["pred"]) < 2 * FP32_TOL
+    pm, tm = spec.transform_to_metric_space(pred2.cpu()), spec.transform_to_metric_space(case["target"])
+    for fn, key in ((lambda: oc.ade(tm, pm), "ade"), (lambda: oc.fde(tm, pm), "fde"), (lambda: oc.apd(pm), "apd")):
+        assert torch.allclose(fn(), case[key], atol=5e-5, rtol=1e-4), key
+    # (a11) training-loss entry point
+    xq = diff.q_sample(case["x_start"].to(d), case["t_loss"].to(d), case["noise_loss"].to(d))
+    assert G.rel_err(xq.cpu(), case["q_sample"]) < FP32_TOL
+    loss, lw, mout = diff.p_losses(case["x_start"].to(d), case["t_loss"].to(d), noise=case["noise_loss"].to(d), x_cond=case["z_past"].to(d))
+    assert G.rel_err(mout.cpu(), case["loss_model_out"]) < FP32_TOL
+    assert G.rel_err(loss.cpu(), case["loss"]) < FP32_TOL
+    assert torch.allclose(lw.cpu().reshape(-1), case["loss_weight"].reshape(-1))
+
+
+# ------------------------------------------------------------------------------------------------
+# edge cases and full-size, size-independent properties
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("batch", [1, 127, 129])
+def test_ragged_batches_match_oracle(cuda_device, batch):
+    case = G.load_npz("h36m_perturbed")
+    spec, ae, diff, ae_sd, diff_sd = G.dataset_models(case, device=cuda_device)
+    cfg = G.dataset_cfg(spec)
+    g = torch.Generator().manual_seed(batch)
+    x = torch.randn(batch, spec.num_nodes, 96, generator=g)
+    cond = torch.tanh(torch.randn(batch, spec.num_nodes, 96, generator=g))
+    t = torch.randint(0, 10, (batch,), generator=g)
+    ref = oc.denoiser_forward(diff_sd, cfg, x[:3], t[:3], cond[:3], prefix="model.")
+    out = diff.model(x.to(cuda_device), t.to(cuda_device), None, cond.to(cuda_device))
+    assert G.rel_err(out[:3].cpu(), ref) < FP32_TOL
+    assert torch.isfinite(out).all()
+
+
+def test_full_size_batch_independence(cuda_device):
+    """BASELINE eval geometry (512 windows x 50 samples = 25 600 latents): every row of the big batch must equal
+    the same row sampled in a small batch (no cross-sample coupling), the t=0 output is clamped, and
+    the first rows still match the reference's golden latents."""
+    case = G.load_npz("amass_perturbed")
+    spec, ae, diff, _, _ = G.dataset_models(case, device=cuda_device)
+    d = cuda_device
+    W, S, N, T = 512, 50, spec.num_nodes, 10
+    B = W * S
+    g = torch.Generator(device="cpu").manual_seed(7)
+    zp = torch.tanh(torch.randn(W, N, 96, generator=g)).to(d)
+    zp[:2] = case["z_past"].to(d)
+    start = torch.randn(B, N, 96, generator=g).to(d)
+    noise = torch.randn(B, T - 1, N, 96, generator=g).to(d)
+    # rows (window 0, samples 0..2) and (window 1, samples 0..2) replay the golden case
+    gs, gn = case["start_noise"].to(d), case["sampling_noise"].to(d)
+    idx = torch.tensor([0, 1, 2, S, S + 1, S + 2], device=d)
+    start[idx], noise[idx] = gs, gn
+    lat, _ = diff.sample(batch_size=B, x_cond=zp, start_noise=start, sampling_noise=noise)
+    assert lat.shape == (B, N, 96) and torch.isfinite(lat).all()
+    assert float(lat.abs().max()) <= 1.0 + 1e-6
+    assert G.rel_err(lat[idx].cpu(), case["latents"]) < FP32_TOL
+    rows = torch.tensor([5 * S + 3, 5 * S + 4, 300 * S + 49, 511 * S], device=d)     # windows 5, 5, 300, 511
+    small, _ = diff.sample(batch_size=4, x_cond=zp[torch.tensor([5, 5, 300, 511], device=d)], start_noise=start[rows].clone(),
+                           sampling_noise=noise[rows].clone())
+    assert G.rel_err(lat[rows].cpu(), small.cpu()) < 1e-5
+
+
+def test_step_kernel_linearity_full_size(cuda_device):
+    """The step is linear in (x_t, eps) once x0 is fixed: step(a x + b y) = a step(x) + b step(y) at x0 = 0."""
+    case = G.load_npz("amass_perturbed")
+    spec, ae, diff, _, _ = G.dataset_models(case, device=cuda_device)
+    B, N = 25600, spec.num_nodes
+    g = torch.Generator(device=cuda_device).manual_seed(11)
+    x, y, e1, e2 = (torch.randn(B, N, 96, device=cuda_device, generator=g) for _ in range(4))
+    z = torch.zeros_like(x)
+    s1, _ = diff._reverse_step(x, z, e1, 5)
+    s2, _ = diff._reverse_step(y, z, e2, 5)
+    s3, _ = diff._reverse_step(2.0 * x - 0.5 * y, z, 2.0 * e1 - 0.5 * e2, 5)
+    assert G.rel_err(s3.cpu(), (2.0 * s1 - 0.5 * s2).cpu()) < 1e-5
+
+
+def test_cpu_tensor_is_rejected(cuda_device):
+    import skeletondiffusion_b200 as sdb
+    nv = _native()
+    layer = sdb.StaticGraphLinear(8, 8, num_nodes=4).to(cuda_device)
+    with pytest.raises(nv.NativeError):
+        layer(torch.zeros(2, 4, 8))
