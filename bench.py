@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--windows", type=int, default=512, help="observed windows per GPU per step (configs/config_eval/config.yaml:27)")
     ap.add_argument("--samples", type=int, default=50)
     ap.add_argument("--precision", default=os.environ.get("SKELDIFF_PRECISION", "fp32"), choices=["fp32", "bf16", "bf16x3"])
-    ap.add_argument("--cpu-windows", type=int, default=2, help="windows of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-windows", type=int, default=64, help="windows of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--perturbed", action="store_true", help="dense non-identity graph-influence matrices (trained-model-like)")
     return ap.parse_args()

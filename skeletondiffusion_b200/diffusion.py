@@ -174,7 +174,9 @@ class NonisotropicGaussianDiffusion(LatentDiffusion):
                  diffusion_covariance_type="skeleton-diffusion", loss_reduction_type="l1", gamma_scheduler="cosine", **kwargs):
         super().__init__(**kwargs)
         Sigma_N, Lambda_N, U = Sigma_N.detach().cpu().float(), Lambda_N.detach().cpu().float(), U.detach().cpu().float()
-        reg = lambda name, val: self.register_buffer(name, val.to(torch.float32))
+        # torch.linalg.eigh returns U in column-major strides: every derived table would inherit them, and the
+        # kernels take raw pointers, so all buffers are registered row-major contiguous
+        reg = lambda name, val: self.register_buffer(name, val.to(torch.float32).contiguous())
         reg("Lambda_N", Lambda_N)
         reg("Sigma_N", Sigma_N)
         reg("U", U)
@@ -259,9 +261,10 @@ class NonisotropicGaussianDiffusion(LatentDiffusion):
         x_start, noise = x_start.float().contiguous(), noise.float().contiguous()
         b, n, d = x_start.shape
         out = torch.empty_like(x_start)
-        nv.check(nv.load().sd_q_sample(x_start.data_ptr(), noise.data_ptr(), t.to(torch.int32).contiguous().data_ptr(),
-                                       self.sqrt_alphas_cumprod.data_ptr(), self.Umm_sqrt_Lambda_bar_t.data_ptr(), out.data_ptr(),
-                                       b, n, d, nv.stream_ptr(x_start.device)), "sd_q_sample")
+        t32 = t.to(x_start.device, torch.int32).contiguous()
+        sqrt_ac, m = self.sqrt_alphas_cumprod.contiguous(), self.Umm_sqrt_Lambda_bar_t.contiguous()
+        nv.check(nv.load().sd_q_sample(x_start.data_ptr(), noise.data_ptr(), t32.data_ptr(), sqrt_ac.data_ptr(), m.data_ptr(),
+                                       out.data_ptr(), b, n, d, nv.stream_ptr(x_start.device)), "sd_q_sample")
         return out
 
     def p_losses(self, x_start, t, noise=None, x_cond=None, n_train_samples=1):
@@ -279,9 +282,11 @@ class NonisotropicGaussianDiffusion(LatentDiffusion):
         loss = torch.empty(x_start.shape[0], device=x_start.device, dtype=torch.float32)
         if self.loss_reduction_type != "l1":
             raise NotImplementedError("loss_reduction_type 'mse'")
-        nv.check(nv.load().sd_mahalanobis_loss(model_out.data_ptr(), x_start.data_ptr(), t.to(torch.int32).contiguous().data_ptr(),
-                                               self.mahalanobis_S_sqrt_recip.data_ptr(), loss.data_ptr(), x_start.shape[0], n, d,
-                                               nv.stream_ptr(x_start.device)), "sd_mahalanobis_loss")
+        t32 = t.to(x_start.device, torch.int32).contiguous()
+        s_tab = self.mahalanobis_S_sqrt_recip.contiguous()
+        nv.check(nv.load().sd_mahalanobis_loss(model_out.data_ptr(), x_start.data_ptr(), t32.data_ptr(), s_tab.data_ptr(),
+                                               loss.data_ptr(), x_start.shape[0], n, d, nv.stream_ptr(x_start.device)),
+                 "sd_mahalanobis_loss")
         return loss, _extract(self.loss_weight, t.view(b, -1)[:, 0], loss.shape[0:1]), model_out
 
     # ------------------------------------------------------------------ reverse process

@@ -57,7 +57,7 @@ def readme_models(case, device="cpu", precision="fp32"):
         sd = {k[2:]: v.clone() for k, v in case.items() if k.startswith("w_")}
         sd.update({k: v.clone() for k, v in tabs.items()})
     else:
-        sd = synth_state_dict(diff.state_dict(), seed=int(case["seed"]), mode="perturbed", gain=GAIN)
+        sd = synth_state_dict(diff.state_dict(), seed=int(case["seed"]), mode="perturbed", gain=float(case["gain"]))
         sd.update({k: v.clone() for k, v in tabs.items()})
     diff.load_state_dict(sd, strict=True)
     return diff.to(device).eval(), sd, corr

@@ -212,7 +212,7 @@ def test_full_size_batch_independence(cuda_device):
     start[idx], noise[idx] = gs, gn
     lat, _ = diff.sample(batch_size=B, x_cond=zp, start_noise=start, sampling_noise=noise)
     assert lat.shape == (B, N, 96) and torch.isfinite(lat).all()
-    assert float(lat.abs().max()) <= 1.0 + 1e-6
+    assert float(lat.abs().max()) <= 1.0 + 1e-5          # t=0: C1 = I up to 6e-7
     assert G.rel_err(lat[idx].cpu(), case["latents"]) < FP32_TOL
     rows = torch.tensor([5 * S + 3, 5 * S + 4, 300 * S + 49, 511 * S], device=d)     # windows 5, 5, 300, 511
     small, _ = diff.sample(batch_size=4, x_cond=zp[torch.tensor([5, 5, 300, 511], device=d)], start_noise=start[rows].clone(),
