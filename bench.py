@@ -170,15 +170,27 @@ def kernel_roofline(dev, spec, diff, precision, peaks):
         torch.cuda.synchronize(dev)
         return sum(ev[i].elapsed_time(ev[i + 1]) for i in range(iters)) / iters * 1e-3
 
-    t_glin = timed(lambda: plan.forward(x, act=nv.ACT_TANH, residual=res, out=out, precision=precision))
     flops = 2.0 * B * N * C * C
-    elem = 4 if precision == "fp32" else 2
-    bytes_glin = B * N * C * elem * 3.0        # read x, read residual, write out
-    tf = flops / t_glin / 1e12
-    roof = {"kernel": "graph-linear 192->192 (+tanh +residual), B=25600, N=%d" % N, "bound": "tensor", "achieved": tf,
-            "peak": peaks.get("bf16_tflops", 1590.0), "unit": "TFLOP/s", "frac": tf / peaks.get("bf16_tflops", 1590.0),
-            "traffic": None, "ms": t_glin * 1e3, "hbm_gbs": bytes_glin / t_glin / 1e9,
-            "peak_source": "MEASURED_PEAKS.json" if peaks.get("_measured") else "fallback"}
+    src = "MEASURED_PEAKS.json" if peaks.get("_measured") else "fallback"
+    if precision == "fp32":
+        t_glin = timed(lambda: plan.forward(x, act=nv.ACT_TANH, residual=res, out=out, precision="fp32"))
+        tf = flops / t_glin / 1e12
+        roof = {"kernel": "glin_gemm_fp32_kernel: graph-linear 192->192 (+tanh +residual), FFMA, B=25600, N=%d" % N, "bound": "tensor",
+                "achieved": tf, "peak": peaks.get("bf16_tflops", 1590.0), "unit": "TFLOP/s", "frac": tf / peaks.get("bf16_tflops", 1590.0),
+                "traffic": None, "ms": t_glin * 1e3, "hbm_gbs": B * N * C * 4 * 3.0 / t_glin / 1e9, "peak_source": src}
+    else:
+        # tcgen05 kernel on its native bf16 tensors: K=192 -> 96 FLOP/B, below the B200 ridge => HBM-bound
+        lib = nv.load()
+        x16, r16, o16 = x.to(torch.bfloat16), res.to(torch.bfloat16), torch.empty(B, N, C, device=dev, dtype=torch.bfloat16)
+        ss = torch.zeros(2 * C, device=dev)
+        st = nv.stream_ptr(dev)
+        t_glin = timed(lambda: nv.check(lib.sd_glin_forward_bf16(plan.handle, x16.data_ptr(), None, ss.data_ptr(), nv.ACT_TANH, r16.data_ptr(),
+                                                                 o16.data_ptr(), 0, None, B, st), "sd_glin_forward_bf16"))
+        bytes_glin = B * N * C * 2 * 3.0        # algorithmic: read x, read residual, write out (bf16)
+        gbs = bytes_glin / t_glin / 1e9
+        roof = {"kernel": "glin_tc_kernel (tcgen05/TMEM/TMA): graph-linear 192->192 (+scale/shift +tanh +residual), bf16, B=25600, N=%d" % N,
+                "bound": "hbm", "achieved": gbs, "peak": peaks.get("hbm_gbs", 6650.0), "unit": "GB/s", "frac": gbs / peaks.get("hbm_gbs", 6650.0),
+                "traffic": None, "ms": t_glin * 1e3, "tflops": flops / t_glin / 1e12, "bytes_per_sample_layer": N * C * 2 * 3, "peak_source": src}
     # fused reverse step: 3 reads + 1 write of [B, N, 96] fp32
     x_t, x0, eps = (torch.randn(B, N, 96, device=dev) for _ in range(3))
     t_step = timed(lambda: diff._reverse_step(x_t, x0, eps, 5))

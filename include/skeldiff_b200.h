@@ -98,6 +98,13 @@ typedef struct sd_glin_args {
 
 int sd_glin_forward(const sd_glin* L, const sd_glin_args* args, void* stream);
 
+/* Same layer on bf16 activations kept in HBM (the tensor-core path's native format; contiguous
+ * [B, N, in] / [B, N, out] tensors).  ss_row_dev: one resolved scale/shift row [2*out] or NULL.
+ * scratch_dev (B*N*out floats) is required iff the layer has a non-identity G^. */
+int sd_glin_forward_bf16(const sd_glin* L, const uint16_t* a_dev, const float* row_scale_dev,
+                         const float* ss_row_dev, int act, const uint16_t* residual_dev, void* out_dev,
+                         int out_is_fp32, float* scratch_dev, int batch, void* stream);
+
 /* ------------------------------------------------------------------ node attention ---------
  * replaces Attention.forward's softmax(q k^T) v over nodes (layers/attention.py:125-135)
  *   qkv_dev [B, N, 3*heads*dim_head] (q | k | v, head-major inside each), out [B, N, heads*dim_head]

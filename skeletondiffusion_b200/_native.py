@@ -48,6 +48,7 @@ SIGNATURES = {
     "sd_glin_set_bf16": (_I, [_P, _P, _I]),
     "sd_glin_destroy": (None, [_P]),
     "sd_glin_forward": (_I, [_P, C.POINTER(SdGlinArgs), _P]),
+    "sd_glin_forward_bf16": (_I, [_P, _P, _P, _P, _I, _P, _P, _I, _P, _I, _P]),
     "sd_node_attention": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "sd_row_inv_norm": (_I, [_P, _P, _I64, _I, _P]),
     "sd_time_table": (_I, [_P, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P]),

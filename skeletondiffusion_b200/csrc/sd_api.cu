@@ -43,8 +43,115 @@ static Epilogue no_epilogue(int OUT) {
 }
 static View null_view() { View v; v.ptr = nullptr; v.sb = v.sn = 0; v.rep = 1; v.width = 0; return v; }
 
-// one graph-linear layer through the precision-selected path
-int glin_forward_tc(const sd_glin* L, const GlinCall& c, int precision, cudaStream_t st);   // sd_glin_tc.cu
+// One graph-linear layer with fp32 views through the tcgen05 path (ABI-level entry, used by
+// sd_glin_forward): operands are cast to bf16 in scratch, the product runs on the tensor cores.
+// scratch layout: [bf16 A copy: B*N*K][fp32 Y: B*N*OUT (only for a non-identity G^)]
+static int glin_forward_tc(const sd_glin* L, const GlinCall& c, int precision, cudaStream_t st) {
+    if (precision != SD_PREC_BF16) { set_error("precision %d is not available for this call", precision); return SD_ERR_UNSUPPORTED; }
+    if (c.epi.ss_row_idx) { set_error("tcgen05 path: per-sample time rows are only supported on the fp32 path"); return SD_ERR_UNSUPPORTED; }
+    if (!c.scratch) { set_error("tcgen05 path: scratch required (B*N*(2*in + 4*out) bytes)"); return SD_ERR_INVALID; }
+    if (c.out.sn % 4 || c.out.sb % 4 || c.out.rep != 1) { set_error("tcgen05 path: output view must be 16-byte aligned rows"); return SD_ERR_UNSUPPORTED; }
+    const int N = L->N, K = L->K, OUT = L->OUT;
+    __nv_bfloat16* a16 = reinterpret_cast<__nv_bfloat16*>(c.scratch);
+    float* y = reinterpret_cast<float*>(reinterpret_cast<char*>(c.scratch) + (((size_t)c.B * N * K * 2 + 255) / 256) * 256);
+    int rc = cast_concat_bf16(c.a0, c.a1, a16, c.B, N, st);
+    if (rc) return rc;
+    TcCall t;
+    t.a0.ptr = a16; t.a0.sb = (long long)N * K; t.a0.sn = K; t.a0.width = K;
+    t.a1.ptr = nullptr; t.a1.sb = t.a1.sn = 0; t.a1.width = 0;
+    t.row_scale = c.row_scale; t.res = nullptr; t.res_sb = t.res_sn = 0; t.B = c.B; t.accurate_tanh = 1;
+    if (L->G == nullptr) {
+        t.bias_node = c.epi.bias_node;
+        t.ss = c.epi.ss ? c.epi.ss + (long long)c.epi.ss_row * c.epi.ss_stride : nullptr;
+        t.act = c.epi.act;
+        t.out = c.out.ptr; t.out_fp32 = 1; t.out_sb = c.out.sb; t.out_sn = c.out.sn;
+        rc = glin_tc_launch(L, t, st);
+        if (rc) return rc;
+        if (c.epi.residual.ptr) return add_residual_fp32(c.out.ptr, c.epi.residual, c.B, N, OUT, c.out.sb, c.out.sn, st);
+        return SD_OK;
+    }
+    t.bias_node = nullptr; t.ss = nullptr; t.act = SD_ACT_NONE;
+    t.out = y; t.out_fp32 = 1; t.out_sb = (long long)N * OUT; t.out_sn = OUT;
+    rc = glin_tc_launch(L, t, st);
+    if (rc) return rc;
+    Epilogue e = c.epi; e.OUT = OUT;
+    return node_mix_fp32(L->G, N, OUT, y, (long long)N * OUT, nullptr, e, c.out, c.B, st);
+}
+
+// Denoiser forward with bf16 activations end to end (tcgen05 graph-linears, bf16 attention I/O).
+// Only the latent input (fp32, cast once) and the x0 output (fp32, feeds the reverse-step kernel) are fp32.
+static int denoiser_forward_bf16(const sd_denoiser* d, const sd_view* x, const sd_view* x_cond, const int32_t* t_rows_dev,
+                                 int t_row, float* out_dev, int B, void* workspace_dev, cudaStream_t st) {
+    if (t_rows_dev) { set_error("bf16 path: per-sample time rows are only supported on the fp32 path"); return SD_ERR_UNSUPPORTED; }
+    const int N = d->N, C = d->C, hd = d->heads * d->dim_head, Kin = d->dim + d->cond_dim;
+    const size_t rows = (size_t)B * N;
+    char* base = static_cast<char*>(workspace_dev);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char* r = base + off; off += (bytes + 255) / 256 * 256; return r; };
+    auto h16 = [&](size_t n) { return reinterpret_cast<__nv_bfloat16*>(take(n * 2)); };
+    __nv_bfloat16 *xin = h16(rows * Kin), *r = h16(rows * C), *xb = h16(rows * C), *h = h16(rows * C), *res = h16(rows * C);
+    __nv_bfloat16 *qkv = h16(rows * 3 * hd), *att = h16(rows * hd);
+    float* inv = reinterpret_cast<float*>(take(rows * 4));
+    float* y = reinterpret_cast<float*>(take(rows * (size_t)(3 * hd > C ? 3 * hd : C) * 4));
+    const int n_pairs = 2 * d->depth;
+    const long long ss_stride = (long long)(n_pairs + 1) * 2 * C;
+    auto tc = [&](const sd_glin* L, const __nv_bfloat16* a0, int k0, const __nv_bfloat16* a1, int k1, const float* row_scale,
+                  int ss_head, int act, const __nv_bfloat16* resid, void* out, int out_fp32) -> int {
+        if (!L) { set_error("graph-linear layer not set"); return SD_ERR_INVALID; }
+        TcCall t;
+        t.a0.ptr = a0; t.a0.sb = (long long)N * k0; t.a0.sn = k0; t.a0.width = k0;
+        t.a1.ptr = a1; t.a1.sb = (long long)N * k1; t.a1.sn = k1; t.a1.width = k1;
+        t.row_scale = row_scale; t.B = B; t.accurate_tanh = 0;
+        const float* ss = ss_head >= 0 ? d->time_table + (long long)t_row * ss_stride + (long long)ss_head * 2 * C : nullptr;
+        if (L->G == nullptr) {
+            t.bias_node = L->bias_node; t.ss = ss; t.act = act;
+            t.res = resid; t.res_sb = (long long)N * L->OUT; t.res_sn = L->OUT;
+            t.out = out; t.out_fp32 = out_fp32; t.out_sb = (long long)N * L->OUT; t.out_sn = L->OUT;
+            return glin_tc_launch(L, t, st);
+        }
+        t.bias_node = nullptr; t.ss = nullptr; t.act = SD_ACT_NONE; t.res = nullptr; t.res_sb = t.res_sn = 0;
+        t.out = y; t.out_fp32 = 1; t.out_sb = (long long)N * L->OUT; t.out_sn = L->OUT;
+        int rc = glin_tc_launch(L, t, st);
+        if (rc) return rc;
+        Epilogue e = no_epilogue(L->OUT);
+        e.bias_node = L->bias_node;
+        if (ss) { e.ss = ss; e.ss_row = 0; e.ss_stride = 0; }
+        e.act = act;
+        return node_mix_to_bf16(L->G, N, L->OUT, y, e, resid, out, out_fp32, B, st);
+    };
+    View vx = make_view(*x);
+    int rc = d->cond_dim > 0 ? cast_concat_bf16(make_view(*x_cond), vx, xin, B, N, st) : cast_concat_bf16(vx, null_view(), xin, B, N, st);
+    if (rc) return rc;
+    rc = tc(d->slot[0], xin, Kin, nullptr, 0, nullptr, -1, SD_ACT_NONE, nullptr, r, 0);
+    if (rc) return rc;
+    const __nv_bfloat16* cur = r;
+    for (int i = 0; i < n_pairs; ++i) {
+        const int s0 = 1 + 4 * i;
+        rc = tc(d->slot[s0], cur, C, nullptr, 0, nullptr, i, SD_ACT_TANH, nullptr, h, 0);
+        if (rc) return rc;
+        rc = tc(d->slot[s0 + 1], h, C, nullptr, 0, nullptr, -1, SD_ACT_TANH, cur, xb, 0);
+        if (rc) return rc;
+        cur = xb;
+        if (i != n_pairs - 1) {
+            rc = row_inv_norm_bf16(xb, inv, (long long)rows, C, st);
+            if (rc) return rc;
+            rc = tc(d->slot[s0 + 2], xb, C, nullptr, 0, inv, -1, SD_ACT_NONE, nullptr, qkv, 0);
+            if (rc) return rc;
+            rc = node_attention_bf16(qkv, att, B, N, d->heads, d->dim_head, st);
+            if (rc) return rc;
+            rc = tc(d->slot[s0 + 3], att, hd, nullptr, 0, nullptr, -1, SD_ACT_NONE, xb, xb, 0);
+            if (rc) return rc;
+        }
+    }
+    const int sf = 1 + 8 * d->depth;
+    rc = tc(d->slot[sf + 2], cur, C, r, C, nullptr, -1, SD_ACT_NONE, nullptr, res, 0);
+    if (rc) return rc;
+    rc = tc(d->slot[sf], cur, C, r, C, nullptr, n_pairs, SD_ACT_TANH, nullptr, h, 0);
+    if (rc) return rc;
+    rc = tc(d->slot[sf + 1], h, C, nullptr, 0, nullptr, -1, SD_ACT_TANH, res, xb, 0);
+    if (rc) return rc;
+    return tc(d->slot[sf + 3], xb, C, nullptr, 0, nullptr, -1, SD_ACT_NONE, nullptr, out_dev, 1);
+}
 
 static int run_glin(const sd_glin* L, GlinCall c, int precision, cudaStream_t st) {
     if (!L) { set_error("graph-linear layer not set"); return SD_ERR_INVALID; }
@@ -115,6 +222,32 @@ int sd_glin_forward(const sd_glin* L, const sd_glin_args* a, void* stream) {
     return run_glin(L, c, a->precision, static_cast<cudaStream_t>(stream));
 }
 
+int sd_glin_forward_bf16(const sd_glin* L, const uint16_t* a_dev, const float* row_scale_dev, const float* ss_row_dev, int act,
+                         const uint16_t* residual_dev, void* out_dev, int out_is_fp32, float* scratch_dev, int batch, void* stream) {
+    if (!L || !a_dev || !out_dev) { set_error("sd_glin_forward_bf16: null argument"); return SD_ERR_INVALID; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int N = L->N, K = L->K, OUT = L->OUT;
+    TcCall t;
+    t.a0.ptr = reinterpret_cast<const __nv_bfloat16*>(a_dev); t.a0.sb = (long long)N * K; t.a0.sn = K; t.a0.width = K;
+    t.a1.ptr = nullptr; t.a1.sb = t.a1.sn = 0; t.a1.width = 0;
+    t.row_scale = row_scale_dev; t.B = batch; t.accurate_tanh = 0;
+    const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(residual_dev);
+    if (L->G == nullptr) {
+        t.bias_node = L->bias_node; t.ss = ss_row_dev; t.act = act;
+        t.res = res; t.res_sb = (long long)N * OUT; t.res_sn = OUT;
+        t.out = out_dev; t.out_fp32 = out_is_fp32; t.out_sb = (long long)N * OUT; t.out_sn = OUT;
+        return glin_tc_launch(L, t, st);
+    }
+    if (!scratch_dev) { set_error("sd_glin_forward_bf16: scratch required for non-identity G"); return SD_ERR_INVALID; }
+    t.bias_node = nullptr; t.ss = nullptr; t.act = SD_ACT_NONE; t.res = nullptr; t.res_sb = t.res_sn = 0;
+    t.out = scratch_dev; t.out_fp32 = 1; t.out_sb = (long long)N * OUT; t.out_sn = OUT;
+    int rc = glin_tc_launch(L, t, st);
+    if (rc) return rc;
+    Epilogue e = no_epilogue(OUT);
+    e.bias_node = L->bias_node; e.ss = ss_row_dev; e.act = act;
+    return node_mix_to_bf16(L->G, N, OUT, scratch_dev, e, res, out_dev, out_is_fp32, batch, st);
+}
+
 int sd_node_attention(const float* qkv_dev, float* out_dev, int batch, int num_nodes, int heads, int dim_head, void* stream) {
     return node_attention_fp32(qkv_dev, out_dev, batch, num_nodes, heads, dim_head, static_cast<cudaStream_t>(stream));
 }
@@ -182,6 +315,8 @@ int sd_denoiser_forward(const sd_denoiser* d, const sd_view* x, const sd_view* x
     if (!t_rows_dev && (t_row < 0 || t_row >= d->time_rows)) { set_error("sd_denoiser_forward: time row %d outside table of %d rows", t_row, d->time_rows); return SD_ERR_INVALID; }
     if ((d->cond_dim > 0) != (x_cond != nullptr && x_cond->ptr != nullptr)) { set_error("sd_denoiser_forward: x_cond presence does not match cond_dim=%d", d->cond_dim); return SD_ERR_INVALID; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (precision == SD_PREC_BF16) return denoiser_forward_bf16(d, x, x_cond, t_rows_dev, t_row, out_dev, batch, workspace_dev, st);
+    if (precision != SD_PREC_FP32) { set_error("sd_denoiser_forward: precision %d not available", precision); return SD_ERR_UNSUPPORTED; }
     const int B = batch, N = d->N, C = d->C, hd = d->heads * d->dim_head;
     const size_t rows = (size_t)B * N;
     Arena ar(workspace_dev);

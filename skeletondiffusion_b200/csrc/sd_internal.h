@@ -1,6 +1,7 @@
 // Internal (non-ABI) declarations shared between translation units of libskeldiff_sm100a.
 #pragma once
 #include "sd_common.cuh"
+#include <cuda_bf16.h>
 
 struct sd_glin {
     int N, n_types, K, OUT;
@@ -63,6 +64,28 @@ int q_sample_fp32(const float* x0, const float* eps, const int* t, const float* 
                   int B, int N, int D, cudaStream_t st);
 int mahalanobis_loss_fp32(const float* out, const float* x0, const int* t, const float* S, float* loss,
                           int B, int N, int D, cudaStream_t st);
+// ---- tensor-core (tcgen05) path: bf16 activations
+struct TcOperand { const __nv_bfloat16* ptr; long long sb, sn; int width; };
+struct TcCall {
+    TcOperand a0, a1;            // K segments (a1.ptr null if unused), rows (b, n) at ptr + b*sb + n*sn
+    const float* row_scale;      // [B*N] or null
+    const float* bias_node;      // [N][OUT] or null
+    const float* ss;             // resolved scale/shift row: scale at [o], shift at [OUT+o]; or null
+    int act;
+    const __nv_bfloat16* res; long long res_sb, res_sn;
+    void* out; int out_fp32; long long out_sb, out_sn;
+    int B;
+    int accurate_tanh;
+};
+bool glin_tc_supported(int K0, int K1, int OUT);
+int glin_tc_launch(const sd_glin* L, const TcCall& c, cudaStream_t st);
+int cast_concat_bf16(const View& a0, const View& a1, __nv_bfloat16* out, int B, int N, cudaStream_t st);
+int row_inv_norm_bf16(const __nv_bfloat16* x, float* inv, long long rows, int width, cudaStream_t st);
+int node_attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int N, int heads, int dh, cudaStream_t st);
+// mix of fp32 raw products with bf16 residual / bf16-or-fp32 output
+int node_mix_to_bf16(const float* G, int N, int OUT, const float* y, const Epilogue& epi, const __nv_bfloat16* res,
+                     void* out, int out_fp32, int B, cudaStream_t st);
+int add_residual_fp32(float* out, const View& res, int B, int N, int OUT, long long out_sb, long long out_sn, cudaStream_t st);
 int gru_gates_fp32(const View& xr, const float* xr_bias, const float* hr, const float* hr_bias,
                    const View& h_in, const ViewW& h_out, int B, int N, int H, cudaStream_t st);
 

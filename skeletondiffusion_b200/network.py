@@ -241,7 +241,10 @@ class Denoiser(nn.Module):
                 raise NotImplementedError("non-integer diffusion times")
         t_int = t.to(torch.int64)
         t_max = int(t_int.max().item()) if t.numel() else 0
-        if t.numel() and int(t_int.min().item()) < 0:
+        t_min = int(t_int.min().item()) if t.numel() else 0
+        if t_min < 0:
             raise ValueError("negative diffusion time")
         plan = self.plan(min_time_rows=t_max + 1)
-        return plan.forward(x, x_cond, t_int.to(torch.int32), precision=precision)
+        # uniform time (every sampling step): one table row for the whole batch, no per-sample gather
+        rows = t_max if t_min == t_max else t_int.to(torch.int32)
+        return plan.forward(x, x_cond, rows, precision=precision)

@@ -71,6 +71,9 @@ class GlinPlan:
         nv.check(nv.load().sd_glin_create(num_nodes, self.types_host, self.n_types, self.in_features, self.out_features,
                                           self.weight.data_ptr(), nv.dptr(self.bias_node), nv.dptr(self.g),
                                           C.byref(self.handle)), "sd_glin_create")
+        # bf16 copy of the weights for the tcgen05 path (K-major [types, out, in], read by TMA)
+        self.weight_bf16 = self.weight.to(torch.bfloat16).contiguous()
+        nv.check(nv.load().sd_glin_set_bf16(self.handle, self.weight_bf16.data_ptr(), 1), "sd_glin_set_bf16")
 
     @classmethod
     def from_layer(cls, layer, fold_in: Optional[torch.Tensor] = None, key=None) -> "GlinPlan":
@@ -114,7 +117,9 @@ class GlinPlan:
         args.residual = nv.view_of(residual)
         args.out = nv.view_of(out)
         scratch = None
-        if not self.identity:
+        if precision != "fp32":       # bf16 operand copy + fp32 raw product (see glin_forward_tc)
+            scratch = Workspace.get(x.device, batch * self.N * (2 * self.in_features + 4 * self.out_features) + 1024, "glin")
+        elif not self.identity:
             scratch = Workspace.get(x.device, batch * self.N * self.out_features * 4, "glin")
         args.scratch_dev = nv.dptr(scratch)
         args.batch = batch
@@ -214,9 +219,13 @@ class DenoiserPlan:
         out = torch.empty(B, self.N, self.out_dim, device=x.device, dtype=torch.float32)
         ws = self.workspace(B, precision)
         xv, cv = nv.view_of(x), nv.view_of(x_cond, rep)
-        t_rows = t_rows.to(x.device, torch.int32).contiguous()
+        if isinstance(t_rows, int):                     # every sample at the same diffusion time (the sampling loop's case)
+            rows_ptr, row0 = None, t_rows
+        else:
+            t_rows = t_rows.to(x.device, torch.int32).contiguous()
+            rows_ptr, row0 = t_rows.data_ptr(), 0
         nv.check(nv.load().sd_denoiser_forward(self.handle, C.byref(xv), C.byref(cv) if x_cond is not None else None,
-                                               t_rows.data_ptr(), 0, out.data_ptr(), B, ws.data_ptr(),
+                                               rows_ptr, row0, out.data_ptr(), B, ws.data_ptr(),
                                                nv.PRECISIONS[precision], nv.stream_ptr(x.device)), "sd_denoiser_forward")
         return out
 
