@@ -1,4 +1,4 @@
-"""Profiling driver: runs the dominant kernels a few times at the full batch (for ncu captures)."""
+"""Profiling driver: runs selected kernels a few times at the full batch (for ncu captures) and prints CUDA-event times."""
 import sys, torch
 sys.path.insert(0, '.')
 import skeletondiffusion_b200 as sdb
@@ -8,18 +8,52 @@ spec = sdb.get_skeleton('amass')
 ae, diff = sdb.build_models(spec, dev)
 lib = nv.load()
 B, N, C = 25600, spec.num_nodes, 192
-plan = diff.model.layers[0][0].block2.proj.plan()
-x16 = torch.randn(B, N, C, device=dev).to(torch.bfloat16)
-r16 = torch.randn(B, N, C, device=dev).to(torch.bfloat16)
+layer = diff.model.layers[0][0].block2.proj
+plan = layer.plan()
+x = torch.randn(B, N, C, device=dev)
+res = torch.randn(B, N, C, device=dev)
+out = torch.empty(B, N, C, device=dev)
+x16, r16 = x.to(torch.bfloat16), res.to(torch.bfloat16)
 o16 = torch.empty_like(x16)
-ss = torch.zeros(2 * C, device=dev)
+ss = torch.zeros(1, 2 * C, device=dev)
 st = nv.stream_ptr(dev)
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 x_t, x0, eps = (torch.randn(B, N, 96, device=dev) for _ in range(3))
-for _ in range(4):
-    if which in ("all", "tc"):
-        nv.check(lib.sd_glin_forward_bf16(plan.handle, x16.data_ptr(), None, ss.data_ptr(), nv.ACT_TANH, r16.data_ptr(), o16.data_ptr(), 0, None, B, st), "tc")
-    if which in ("all", "step"):
-        diff._reverse_step(x_t, x0, eps, 5)
-torch.cuda.synchronize()
-print("done")
+qkv = torch.randn(B, N, 768, device=dev)
+att = torch.empty(B, N, 256, device=dev)
+
+
+def tc():
+    nv.check(lib.sd_glin_forward_bf16(plan.handle, x16.data_ptr(), None, ss.data_ptr(), nv.ACT_TANH, r16.data_ptr(), o16.data_ptr(), 0, None, B, st), "tc")
+
+
+def tc3():
+    plan.forward(x, scale_shift=ss, act=nv.ACT_TANH, residual=res, out=out, precision="bf16x3")
+
+
+def ffma():
+    plan.forward(x, scale_shift=ss, act=nv.ACT_TANH, residual=res, out=out, precision="fp32")
+
+
+def step():
+    diff._reverse_step(x_t, x0, eps, 5)
+
+
+def attn():
+    nv.check(lib.sd_node_attention(qkv.data_ptr(), att.data_ptr(), B, N, 8, 32, st), "attn")
+
+
+fns = {"tc": tc, "tc3": tc3, "ffma": ffma, "step": step, "attn": attn}
+sel = list(fns) if which == "all" else which.split(",")
+for name in sel:
+    fn = fns[name]
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"{name}: {e0.elapsed_time(e1) / 5 * 1e3:.1f} us")

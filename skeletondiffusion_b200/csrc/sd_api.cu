@@ -153,10 +153,28 @@ static int denoiser_forward_bf16(const sd_denoiser* d, const sd_view* x, const s
     return tc(d->slot[sf + 3], xb, C, nullptr, 0, nullptr, -1, SD_ACT_NONE, nullptr, out_dev, 1);
 }
 
+static bool tc3_views_ok(const GlinCall& c) {
+    auto ok = [](const void* p, long long sb, long long sn) { return p == nullptr || ((reinterpret_cast<uintptr_t>(p) & 15u) == 0 && sb % 4 == 0 && sn % 4 == 0); };
+    return ok(c.a0.ptr, c.a0.sb, c.a0.sn) && ok(c.a1.ptr, c.a1.sb, c.a1.sn) && ok(c.out.ptr, c.out.sb, c.out.sn) &&
+           ok(c.epi.residual.ptr, c.epi.residual.sb, c.epi.residual.sn) && c.out.rep == 1;
+}
+
 static int run_glin(const sd_glin* L, GlinCall c, int precision, cudaStream_t st) {
     if (!L) { set_error("graph-linear layer not set"); return SD_ERR_INVALID; }
     if (c.epi.bias_node == nullptr) c.epi.bias_node = L->bias_node;
     c.epi.OUT = L->OUT;
+    if (precision == SD_PREC_BF16X3) {
+        // fp32-grade products on the tensor cores where the shape allows it; otherwise the (exact) FFMA kernel
+        const int K1 = c.a1.ptr ? c.a1.width : 0;
+        if (L->planes == 3 && !c.epi.ss_row_idx && glin_tc3_supported(c.a0.width, K1, L->OUT) && tc3_views_ok(c)) {
+            if (L->G == nullptr) return glin_tc3_launch(L, c, c.out, true, st);
+            if (!c.scratch) { set_error("glin: scratch required for non-identity G"); return SD_ERR_INVALID; }
+            int rc = glin_tc3_launch(L, c, contiguous_view_w(c.scratch, L->N, L->OUT), false, st);
+            if (rc) return rc;
+            return node_mix_fp32(L->G, L->N, L->OUT, c.scratch, (long long)L->N * L->OUT, nullptr, c.epi, c.out, c.B, st);
+        }
+        return glin_forward_fp32(L->W, L->K, L->OUT, L->types, L->N, L->G, c, st);
+    }
     if (precision != SD_PREC_FP32) return glin_forward_tc(L, c, precision, st);
     return glin_forward_fp32(L->W, L->K, L->OUT, L->types, L->N, L->G, c, st);
 }
@@ -316,7 +334,8 @@ int sd_denoiser_forward(const sd_denoiser* d, const sd_view* x, const sd_view* x
     if ((d->cond_dim > 0) != (x_cond != nullptr && x_cond->ptr != nullptr)) { set_error("sd_denoiser_forward: x_cond presence does not match cond_dim=%d", d->cond_dim); return SD_ERR_INVALID; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (precision == SD_PREC_BF16) return denoiser_forward_bf16(d, x, x_cond, t_rows_dev, t_row, out_dev, batch, workspace_dev, st);
-    if (precision != SD_PREC_FP32) { set_error("sd_denoiser_forward: precision %d not available", precision); return SD_ERR_UNSUPPORTED; }
+    if (precision != SD_PREC_FP32 && precision != SD_PREC_BF16X3) { set_error("sd_denoiser_forward: precision %d not available", precision); return SD_ERR_UNSUPPORTED; }
+    if (precision == SD_PREC_BF16X3 && t_rows_dev) precision = SD_PREC_FP32;   // per-sample times: FFMA kernels (both are fp32-grade)
     const int B = batch, N = d->N, C = d->C, hd = d->heads * d->dim_head;
     const size_t rows = (size_t)B * N;
     Arena ar(workspace_dev);

@@ -62,8 +62,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 
 template <int ACT> __device__ __forceinline__ float epi_act(float x) {
     if (ACT == TCA_TANH_FAST) return tanh_fast(x);
-    if (ACT == TCA_TANH) return tanhf(x);
-    if (ACT == TCA_TANH_TANH) return tanhf(tanhf(x));
+    if (ACT == TCA_TANH) return tanh_acc(x);
+    if (ACT == TCA_TANH_TANH) return tanh_acc(tanh_acc(x));
     return x;
 }
 

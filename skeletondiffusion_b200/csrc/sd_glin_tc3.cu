@@ -1,0 +1,358 @@
+// StaticGraphLinear with fp32-grade products on the bf16 tensor cores ("bf16x3").
+//
+// fp32 operands are split into three bf16 planes, x = x0 + x1 + x2 (8 mantissa bits each, exact), and
+//     x . w  ~=  x0 w0 + x0 w1 + x0 w2 + x1 w0 + x1 w1 + x2 w0        (terms below 2^-24 |x||w| dropped)
+// is accumulated in fp32 in TMEM: six tcgen05.mma.kind::f16 per K = 16 step.  Activations stay fp32 in
+// HBM (4 B/element, the whole non-GEMM pipeline of the fp32 path is reused unchanged); the split happens
+// on the way into shared memory:
+//   warps 0-3  transform producers: coalesced LDG.128 of the fp32 tile rows (any sd_view: in-place repeat,
+//              two K segments), split, STS.64 into three SWIZZLE_128B K-major plane tiles, fence.proxy.async
+//   warp 4     TMA loads of the pre-split weight planes (resident per (node, n-tile) group) + MMA issue
+//   warp 5     TMEM allocator
+//   warps 8-11 epilogue: tcgen05.ld, row scale, bias, scale/shift, accurate tanhf, fp32 residual, fp32 store (tanh via tanh_acc)
+// MMA-bound by construction: 6 x 2*K*OUT FLOP per row at the bf16 rate = the cost of an fp32-accurate GEMM
+// on a machine whose TF32 rate is half the bf16 rate.
+//
+// Reference semantics: GraphLinear.forward, src/core/network/layers/graph_structural.py:30-43.
+#include "sd_internal.h"
+#include "sd_tc.cuh"
+#include <cuda.h>
+
+namespace sd {
+
+using namespace sd::tc;
+
+constexpr int T3_BM = 128, T3_BK = 64;
+constexpr int T3_PRODUCERS = 256;   // warps 0-7 (two per scheduler hide each other's LDG latency)
+constexpr int T3_MMA_WARP = 8, T3_ALLOC_WARP = 9, T3_EPI_WARP0 = 12;
+constexpr int T3_THREADS = 512;     // 16 warps x 128 registers
+constexpr int T3_MAX_STAGES = 4;
+constexpr int T3_STAGE_BYTES = 3 * T3_BM * 128;    // three plane tiles of 128 rows x 128 B
+
+struct T3Params {
+    View a0, a1;
+    int B, N, K, OUT, BN, NT, MT, KB, nstage, n_types, tmem_cols;
+    NodeTypes types;
+    const float* row_scale;
+    const float* bias_node;
+    const float* ss;            // resolved scale/shift row or null
+    View residual;              // fp32, ptr null if none
+    ViewW out;
+};
+
+struct __align__(8) T3Barriers {
+    uint64_t full[T3_MAX_STAGES], empty[T3_MAX_STAGES];
+    uint64_t w_full, w_empty;
+    uint64_t acc_full[2], acc_empty[2];
+    uint32_t tmem_base, pad;
+};
+
+// Exact 3-way split by truncation: the 24 significand bits of x fall 8/8/8 into three bf16 values held in the
+// UPPER halves of h, m, l (x == h + m + l exactly).  Pure LOP/FADD: the first version used F2F.BF16.F32
+// (round-to-nearest), whose quarter-rate conversion unit made the producers the bottleneck of the kernel.
+__device__ __forceinline__ void split3(float x, uint32_t& h, uint32_t& m, uint32_t& l) {
+    h = __float_as_uint(x) & 0xFFFF0000u;
+    const float r1 = x - __uint_as_float(h);
+    m = __float_as_uint(r1) & 0xFFFF0000u;
+    const float r2 = r1 - __uint_as_float(m);
+    l = __float_as_uint(r2) & 0xFFFF0000u;
+}
+// (hi16 of b) << 16 | (hi16 of a): two bf16 packed in element order a, b
+__device__ __forceinline__ uint32_t pack_hi(uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x7632); }
+
+template <int ACT, bool HAS_RES>
+__global__ void __launch_bounds__(T3_THREADS, 1)
+glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t w_block = (uint32_t)p.BN * 128u;                 // one (plane, k-block) weight tile
+    uint8_t* w_smem = smem;                                        // [plane][kb][BN x 128 B]
+    uint8_t* a_smem = w_smem + (size_t)3 * p.KB * w_block;         // [stage][plane][128 x 128 B]
+    float* epi_mul = reinterpret_cast<float*>(a_smem + (size_t)p.nstage * T3_STAGE_BYTES);
+    float* epi_add = epi_mul + p.BN;
+    T3Barriers* bars = reinterpret_cast<T3Barriers*>(epi_add + p.BN);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&map_w);
+        for (int s = 0; s < p.nstage; ++s) { mbar_init(&bars->full[s], T3_PRODUCERS); mbar_init(&bars->empty[s], 1); }
+        mbar_init(&bars->w_full, 1);
+        mbar_init(&bars->w_empty, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&bars->acc_full[s], 1); mbar_init(&bars->acc_empty[s], 128); }
+        fence_barrier_init();
+    }
+    if (warp == T3_ALLOC_WARP) tmem_alloc(&bars->tmem_base, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    const long long total = (long long)p.N * p.NT * p.MT;
+    const long long item_lo = total * blockIdx.x / gridDim.x;
+    const long long item_hi = total * (blockIdx.x + 1) / gridDim.x;
+    const int KB0 = p.a0.width / T3_BK;
+
+    if (warp < 8) {
+        // ================================================================ transform producers (256 threads)
+        const int t = threadIdx.x;
+        const int col4 = t & 15;            // which float4 of the 64-wide k-block row
+        const int row0 = t >> 4;            // rows row0 + 16*i, i = 0..7
+        const uint32_t chunk = (uint32_t)(col4 >> 1), half = (uint32_t)(col4 & 1) << 3;
+        int stage = 0; uint32_t phase = 0;
+        for (long long it = item_lo; it < item_hi; ++it) {
+            const long long g = it / p.MT;
+            const int mt = (int)(it % p.MT);
+            const int node = (int)(g / p.NT);
+            for (int kb = 0; kb < p.KB; ++kb) {
+                const View& seg = kb < KB0 ? p.a0 : p.a1;
+                const int koff = (kb < KB0 ? kb : kb - KB0) * T3_BK + col4 * 4;
+                float4 v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int b = mt * T3_BM + row0 + 16 * i;
+                    v[i] = (b < p.B) ? __ldg(reinterpret_cast<const float4*>(row_ptr(seg, b, node) + koff)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                mbar_wait(&bars->empty[stage], phase ^ 1);
+                uint8_t* st = a_smem + (size_t)stage * T3_STAGE_BYTES;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = row0 + 16 * i;
+                    uint32_t h[4], m[4], l[4];
+                    split3(v[i].x, h[0], m[0], l[0]); split3(v[i].y, h[1], m[1], l[1]);
+                    split3(v[i].z, h[2], m[2], l[2]); split3(v[i].w, h[3], m[3], l[3]);
+                    const uint32_t off = (uint32_t)r * 128u + ((chunk ^ (uint32_t)(r & 7)) << 4) + half;
+                    *reinterpret_cast<uint2*>(st + off) = make_uint2(pack_hi(h[0], h[1]), pack_hi(h[2], h[3]));
+                    *reinterpret_cast<uint2*>(st + T3_BM * 128 + off) = make_uint2(pack_hi(m[0], m[1]), pack_hi(m[2], m[3]));
+                    *reinterpret_cast<uint2*>(st + 2 * T3_BM * 128 + off) = make_uint2(pack_hi(l[0], l[1]), pack_hi(l[2], l[3]));
+                }
+                fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
+                mbar_arrive(&bars->full[stage]);
+                if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == T3_MMA_WARP) {
+        // ================================================================ weight TMA + MMA issue
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(T3_BM, (uint32_t)p.BN);
+            int stage = 0; uint32_t phase = 0, acc = 0, acc_phase = 0, w_loads = 0;
+            long long cur_g = -1;
+            for (long long it = item_lo; it < item_hi; ++it) {
+                const long long g = it / p.MT;
+                const int node = (int)(g / p.NT), nt = (int)(g % p.NT);
+                if (g != cur_g) {
+                    // the previous group's MMAs (w_empty phase w_loads-1) must have retired before the tile is overwritten
+                    if (w_loads > 0) mbar_wait(&bars->w_empty, (w_loads - 1) & 1u);
+                    mbar_arrive_expect_tx(&bars->w_full, 3u * (uint32_t)p.KB * w_block);
+                    for (int pl = 0; pl < 3; ++pl)
+                        for (int kb = 0; kb < p.KB; ++kb)
+                            tma_load_3d(w_smem + (size_t)(pl * p.KB + kb) * w_block, &map_w, &bars->w_full, kb * T3_BK, nt * p.BN,
+                                        pl * p.n_types + p.types.t[node]);
+                    mbar_wait(&bars->w_full, w_loads & 1u);
+                    ++w_loads;
+                    cur_g = g;
+                }
+                mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.BN;
+                for (int kb = 0; kb < p.KB; ++kb) {
+                    mbar_wait(&bars->full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_base = smem_u32(a_smem + (size_t)stage * T3_STAGE_BYTES);
+                    uint32_t first = (kb == 0) ? 1u : 0u;
+#pragma unroll
+                    for (int pa = 0; pa < 3; ++pa) {
+#pragma unroll
+                        for (int pw = 0; pw < 3; ++pw) {
+                            if (pa + pw > 2) continue;
+                            const uint64_t adesc = umma_desc_sw128(a_base + (uint32_t)pa * T3_BM * 128);
+                            const uint64_t bdesc = umma_desc_sw128(smem_u32(w_smem + (size_t)(pw * p.KB + kb) * w_block));
+#pragma unroll
+                            for (int k = 0; k < T3_BK / 16; ++k) {
+                                umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, first ? 0u : 1u);
+                                first = 0u;
+                            }
+                        }
+                    }
+                    umma_commit(&bars->empty[stage]);
+                    if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&bars->acc_full[acc]);
+                const bool last_of_group = (it + 1 == item_hi) || ((it + 1) / p.MT != g);
+                if (last_of_group) umma_commit(&bars->w_empty);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= T3_EPI_WARP0) {
+        // ================================================================ epilogue (warps 12-15: warp % 4 = lane quarter)
+        const int quarter = warp & 3;
+        const int et = threadIdx.x - T3_EPI_WARP0 * 32;
+        uint32_t acc = 0, acc_phase = 0;
+        long long cur_g = -1;
+        for (long long it = item_lo; it < item_hi; ++it) {
+            const long long g = it / p.MT;
+            const int mt = (int)(it % p.MT);
+            const int node = (int)(g / p.NT), nt = (int)(g % p.NT);
+            const int o0 = nt * p.BN;
+            if (g != cur_g) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int c = et; c < p.BN; c += 128) {
+                    const int o = o0 + c;
+                    const float mul = p.ss ? (__ldg(p.ss + o) + 1.0f) : 1.0f;
+                    const float bias = p.bias_node ? __ldg(p.bias_node + (long long)node * p.OUT + o) : 0.0f;
+                    epi_mul[c] = mul;
+                    epi_add[c] = fmaf(bias, mul, p.ss ? __ldg(p.ss + p.OUT + o) : 0.0f);
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                cur_g = g;
+            }
+            const int b = mt * T3_BM + quarter * 32 + lane;
+            const bool valid = b < p.B;
+            const float rs = (valid && p.row_scale) ? __ldg(p.row_scale + (long long)b * p.N + node) : 1.0f;
+            const float* res_row = (HAS_RES && valid) ? row_ptr(p.residual, b, node) + o0 : nullptr;
+            float* out_row = valid ? row_ptr(p.out, b, node) + o0 : nullptr;
+            // 16-column chunks; the residual of chunk c+1 is in flight while chunk c is computed and stored
+            float4 rr[4];
+            if (HAS_RES && valid) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) rr[q] = __ldg(reinterpret_cast<const float4*>(res_row) + q);
+            }
+            mbar_wait(&bars->acc_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (uint32_t)p.BN;
+            for (int c0 = 0; c0 < p.BN; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld_32x16(t_row + (uint32_t)c0, v);
+                tmem_ld_wait();
+                float4 o[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 m4 = *reinterpret_cast<const float4*>(epi_mul + c0 + 4 * q);
+                    const float4 a4 = *reinterpret_cast<const float4*>(epi_add + c0 + 4 * q);
+                    o[q].x = fmaf(__uint_as_float(v[4 * q + 0]) * rs, m4.x, a4.x);
+                    o[q].y = fmaf(__uint_as_float(v[4 * q + 1]) * rs, m4.y, a4.y);
+                    o[q].z = fmaf(__uint_as_float(v[4 * q + 2]) * rs, m4.z, a4.z);
+                    o[q].w = fmaf(__uint_as_float(v[4 * q + 3]) * rs, m4.w, a4.w);
+                    if (ACT == SD_ACT_TANH) { o[q].x = tanh_acc(o[q].x); o[q].y = tanh_acc(o[q].y); o[q].z = tanh_acc(o[q].z); o[q].w = tanh_acc(o[q].w); }
+                    if (ACT == SD_ACT_TANH_TANH) {
+                        o[q].x = tanh_acc(tanh_acc(o[q].x)); o[q].y = tanh_acc(tanh_acc(o[q].y));
+                        o[q].z = tanh_acc(tanh_acc(o[q].z)); o[q].w = tanh_acc(tanh_acc(o[q].w));
+                    }
+                    if (HAS_RES) { o[q].x += rr[q].x; o[q].y += rr[q].y; o[q].z += rr[q].z; o[q].w += rr[q].w; }
+                }
+                if (HAS_RES && valid && c0 + 16 < p.BN) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) rr[q] = __ldg(reinterpret_cast<const float4*>(res_row + c0 + 16) + q);
+                }
+                if (valid) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(out_row + c0 + 4 * q) = o[q];
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&bars->acc_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == T3_ALLOC_WARP) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static size_t t3_fixed_smem(int K, int bn) { return (size_t)3 * (K / T3_BK) * bn * 128 + 2 * (size_t)bn * 4 + sizeof(T3Barriers) + 1024; }
+static int t3_stages(int K, int bn) {
+    const size_t budget = 227 * 1024, fixed = t3_fixed_smem(K, bn);
+    if (fixed + 2 * (size_t)T3_STAGE_BYTES > budget) return 0;
+    const size_t n = (budget - fixed) / T3_STAGE_BYTES;
+    return (int)(n > T3_MAX_STAGES ? T3_MAX_STAGES : n);
+}
+static int t3_pick_bn(int K, int OUT) {
+    const int cands[] = {192, 128, 96, 64, 32};
+    for (int bn : cands) if (OUT % bn == 0 && t3_stages(K, bn) >= 2) return bn;
+    return 0;
+}
+
+bool glin_tc3_supported(int K0, int K1, int OUT) {
+    if (K0 <= 0 || K0 % T3_BK || K1 % T3_BK) return false;
+    return t3_pick_bn(K0 + K1, OUT) != 0;
+}
+
+template <int ACT, bool HAS_RES>
+static int t3_launch_t(const CUtensorMap& mw, const T3Params& p, int grid, size_t smem, cudaStream_t st) {
+    auto kern = glin_tc3_kernel<ACT, HAS_RES>;
+    static bool configured = false;
+    if (!configured) {
+        SD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        configured = true;
+    }
+    kern<<<grid, T3_THREADS, smem, st>>>(mw, p);
+    SD_LAUNCH_OK("glin_tc3_kernel");
+    return SD_OK;
+}
+
+// out = epilogue(A @ W^T) with fp32 views; the caller guarantees G == identity for this call
+int glin_tc3_launch(const sd_glin* L, const GlinCall& c, const ViewW& out, bool apply_epilogue, cudaStream_t st) {
+    if (!L->W_bf16 || L->planes != 3) { set_error("bf16x3 path: 3-plane weights not set on this layer"); return SD_ERR_INVALID; }
+    const int K0 = c.a0.width, K1 = c.a1.ptr ? c.a1.width : 0;
+    if (K0 + K1 != L->K || !glin_tc3_supported(K0, K1, L->OUT)) { set_error("bf16x3 path: unsupported shape K=%d+%d OUT=%d", K0, K1, L->OUT); return SD_ERR_UNSUPPORTED; }
+    if (c.epi.ss_row_idx && apply_epilogue) { set_error("bf16x3 path: per-sample time rows are only supported on the FFMA path"); return SD_ERR_UNSUPPORTED; }
+    if (c.B <= 0) return SD_OK;
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    auto view_ok = [&](const View& v) { return v.ptr == nullptr || (al16(v.ptr) && v.sb % 4 == 0 && v.sn % 4 == 0); };
+    if (!view_ok(c.a0) || !view_ok(c.a1) || !al16(out.ptr) || out.sb % 4 || out.sn % 4 ||
+        (apply_epilogue && c.epi.residual.ptr && !view_ok(c.epi.residual))) {
+        set_error("bf16x3 path: operands must be 16-byte aligned");
+        return SD_ERR_UNSUPPORTED;
+    }
+    T3Params p;
+    p.a0 = c.a0; p.a1 = c.a1; if (!c.a1.ptr) { p.a1 = c.a0; p.a1.width = 0; }
+    p.B = c.B; p.N = L->N; p.K = L->K; p.OUT = L->OUT; p.BN = t3_pick_bn(L->K, L->OUT); p.NT = L->OUT / p.BN;
+    p.MT = (c.B + T3_BM - 1) / T3_BM; p.KB = L->K / T3_BK; p.nstage = t3_stages(L->K, p.BN); p.n_types = L->n_types;
+    p.tmem_cols = 2 * p.BN <= 32 ? 32 : (2 * p.BN <= 64 ? 64 : (2 * p.BN <= 128 ? 128 : (2 * p.BN <= 256 ? 256 : 512)));
+    p.types = L->types;
+    p.out = out;
+    int act = SD_ACT_NONE;
+    bool has_res = false;
+    if (apply_epilogue) {
+        p.row_scale = c.row_scale; p.bias_node = c.epi.bias_node;
+        p.ss = c.epi.ss ? c.epi.ss + (long long)c.epi.ss_row * c.epi.ss_stride : nullptr;
+        p.residual = c.epi.residual; act = c.epi.act; has_res = c.epi.residual.ptr != nullptr;
+    } else {
+        p.row_scale = c.row_scale; p.bias_node = nullptr; p.ss = nullptr; p.residual.ptr = nullptr; p.residual.sb = p.residual.sn = 0; p.residual.rep = 1; p.residual.width = 0;
+    }
+    // weight planes: [3][types][OUT][K] bf16 -> 3-D map (K, OUT, 3*types)
+    static EncodeTiledFn3 enc = nullptr;
+    if (!enc) {
+        void* fp = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            set_error("cuTensorMapEncodeTiled unavailable"); return SD_ERR_CUDA;
+        }
+        enc = reinterpret_cast<EncodeTiledFn3>(fp);
+    }
+    CUtensorMap mw;
+    cuuint64_t dims[3] = {(cuuint64_t)L->K, (cuuint64_t)L->OUT, (cuuint64_t)(3 * L->n_types)};
+    cuuint64_t strides[2] = {(cuuint64_t)L->K * 2, (cuuint64_t)L->OUT * L->K * 2};
+    cuuint32_t box[3] = {(cuuint32_t)T3_BK, (cuuint32_t)p.BN, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&mw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<uint16_t*>(L->W_bf16), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (weights x3) failed: %d", (int)r); return SD_ERR_CUDA; }
+    const size_t smem = t3_fixed_smem(L->K, p.BN) + (size_t)p.nstage * T3_STAGE_BYTES;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long total = (long long)p.N * p.NT * p.MT;
+    const int grid = (int)(total < sms ? total : sms);
+    if (act == SD_ACT_NONE) return has_res ? t3_launch_t<SD_ACT_NONE, true>(mw, p, grid, smem, st) : t3_launch_t<SD_ACT_NONE, false>(mw, p, grid, smem, st);
+    if (act == SD_ACT_TANH) return has_res ? t3_launch_t<SD_ACT_TANH, true>(mw, p, grid, smem, st) : t3_launch_t<SD_ACT_TANH, false>(mw, p, grid, smem, st);
+    if (act == SD_ACT_TANH_TANH) return has_res ? t3_launch_t<SD_ACT_TANH_TANH, true>(mw, p, grid, smem, st) : t3_launch_t<SD_ACT_TANH_TANH, false>(mw, p, grid, smem, st);
+    set_error("bf16x3 path: unknown activation %d", act);
+    return SD_ERR_INVALID;
+}
+
+}  // namespace sd

@@ -77,6 +77,8 @@ struct TcCall {
     int B;
     int accurate_tanh;
 };
+bool glin_tc3_supported(int K0, int K1, int OUT);
+int glin_tc3_launch(const sd_glin* L, const GlinCall& c, const ViewW& out, bool apply_epilogue, cudaStream_t st);
 bool glin_tc_supported(int K0, int K1, int OUT);
 int glin_tc_launch(const sd_glin* L, const TcCall& c, cudaStream_t st);
 int cast_concat_bf16(const View& a0, const View& a1, __nv_bfloat16* out, int B, int N, cudaStream_t st);

@@ -71,9 +71,14 @@ class GlinPlan:
         nv.check(nv.load().sd_glin_create(num_nodes, self.types_host, self.n_types, self.in_features, self.out_features,
                                           self.weight.data_ptr(), nv.dptr(self.bias_node), nv.dptr(self.g),
                                           C.byref(self.handle)), "sd_glin_create")
-        # bf16 copy of the weights for the tcgen05 path (K-major [types, out, in], read by TMA)
-        self.weight_bf16 = self.weight.to(torch.bfloat16).contiguous()
-        nv.check(nv.load().sd_glin_set_bf16(self.handle, self.weight_bf16.data_ptr(), 1), "sd_glin_set_bf16")
+        # bf16 weight planes for the tcgen05 paths (K-major [3, types, out, in], read by TMA): w = p0 + p1 + p2 exactly;
+        # plane 0 alone (= bf16(w)) is what the plain bf16 path multiplies with
+        p0 = self.weight.to(torch.bfloat16)
+        r1 = self.weight - p0.float()
+        p1 = r1.to(torch.bfloat16)
+        p2 = (r1 - p1.float()).to(torch.bfloat16)
+        self.weight_bf16 = torch.stack([p0, p1, p2], 0).contiguous()
+        nv.check(nv.load().sd_glin_set_bf16(self.handle, self.weight_bf16.data_ptr(), 3), "sd_glin_set_bf16")
 
     @classmethod
     def from_layer(cls, layer, fold_in: Optional[torch.Tensor] = None, key=None) -> "GlinPlan":
@@ -117,7 +122,7 @@ class GlinPlan:
         args.residual = nv.view_of(residual)
         args.out = nv.view_of(out)
         scratch = None
-        if precision != "fp32":       # bf16 operand copy + fp32 raw product (see glin_forward_tc)
+        if precision == "bf16":       # bf16 operand copy + fp32 raw product (see glin_forward_tc)
             scratch = Workspace.get(x.device, batch * self.N * (2 * self.in_features + 4 * self.out_features) + 1024, "glin")
         elif not self.identity:
             scratch = Workspace.get(x.device, batch * self.N * self.out_features * 4, "glin")

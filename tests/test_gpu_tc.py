@@ -116,3 +116,47 @@ def test_bf16_full_batch_matches_small_batch(cuda_device):
     small = diff.model(x[rows].contiguous(), t[:5], None, zp[rows // S].contiguous(), precision="bf16")
     assert torch.isfinite(big).all()
     assert G.rel_err(big[rows], small) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# bf16x3: fp32-grade products on the tensor cores (three bf16 planes, six MMAs per K step)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kin,kout,batch,ident", [(192, 192, 300, True), (192, 768, 130, True), (256, 192, 129, False),
+                                                   (192, 96, 5, True), (384, 192, 200, True)])
+def test_bf16x3_graph_linear_is_fp32_grade(cuda_device, kin, kout, batch, ident):
+    import skeletondiffusion_b200 as sdb
+    from skeletondiffusion_b200 import _native as nv
+    from skeletondiffusion_b200.testing import synth_state_dict
+    spec = sdb.get_skeleton("amass")
+    N, nt = spec.num_nodes, spec.nodes_type_id
+    layer = sdb.StaticGraphLinear(kin, kout, bias=True, num_nodes=N, node_types=nt, learn_influence=True)
+    sd = synth_state_dict(layer.state_dict(), seed=41, mode="perturbed", gain=1.0)
+    if ident:
+        sd["G"] = torch.eye(N)
+    layer.load_state_dict(sd)
+    g = torch.Generator().manual_seed(kin * 7 + kout)
+    x = torch.randn(batch, N, kin, generator=g)
+    res = torch.randn(batch, N, kout, generator=g)
+    ref = torch.tanh(oc.graph_linear(sd, "", x.double().float(), nt, True)) + res
+    ref64 = torch.tanh(oc.graph_linear({k: v.double() for k, v in sd.items()}, "", x.double(), nt, True)) + res.double()
+    d = cuda_device
+    out = layer.to(d).plan().forward(x.to(d), act=nv.ACT_TANH, residual=res.to(d), precision="bf16x3")
+    err, err_ref = G.rel_err(out.cpu().double(), ref64), G.rel_err(ref.double(), ref64)
+    assert err < 3e-6, (err, err_ref)          # as close to the float64 truth as fp32 PyTorch itself (~1e-6)
+
+
+@pytest.mark.parametrize("name", ["amass_perturbed", "h36m_perturbed", "amass_init"])
+def test_bf16x3_pipeline_meets_fp32_gate(cuda_device, name):
+    """The tensor-core fp32-grade path must pass the same <=1e-4 gate as the FFMA path, against the reference's goldens."""
+    import skeletondiffusion_b200 as sdb
+    case = G.load_npz(name)
+    spec, ae, diff, _, _ = G.dataset_models(case, device=cuda_device, precision="bf16x3")
+    d = cuda_device
+    S, W, ph = int(case["samples"]), int(case["windows"]), int(case["ph"])
+    lat, (_, _, mean_t) = diff.sample(batch_size=W * S, x_cond=case["z_past"].to(d), start_noise=case["start_noise"].to(d),
+                                      sampling_noise=case["sampling_noise"].to(d), return_sampling_noise=True)
+    assert G.rel_err(mean_t.cpu(), case["mean_t"]) < 1e-4
+    assert G.rel_err(lat.cpu(), case["latents"]) < 1e-4
+    pred = sdb.get_prediction(case["obs"].to(d), (ae, diff), num_samples=S, pred_length=ph, diffusion_conditioning=True,
+                              sampler_kwargs=dict(start_noise=case["start_noise"].to(d), sampling_noise=case["sampling_noise"].to(d)))
+    assert G.rel_err(pred.cpu(), case["pred"]) < 2e-4
