@@ -78,6 +78,8 @@ int  sd_glin_create(int num_nodes, const int32_t* node_types_host, int n_types, 
                     const float* g_dev, sd_glin** out);
 /* optional bf16 weight planes [planes][n_types, out, in] for the tcgen05 paths (planes = 1 or 3) */
 int  sd_glin_set_bf16(sd_glin* L, const uint16_t* weight_bf16_dev, int planes);
+/* optional K-major fp32 copy [n_types, in, out] that enables the FFMA2 kernel (out % 96 == 0, in % 32 == 0) */
+int  sd_glin_set_kmajor(sd_glin* L, const float* weight_kmajor_dev);
 void sd_glin_destroy(sd_glin* L);
 
 typedef struct sd_glin_args {
@@ -190,6 +192,11 @@ int  sd_gru_create(int num_nodes, const int32_t* node_types_host, int n_types, i
                    int hidden_size, const float* w_ih_dev, const float* w_hh_dev,
                    const float* bias_ih_seq_dev, const float* bias_hh_seq_dev,
                    const float* gx_seq_dev, int steps, sd_gru** out);
+/* Optional, only when every gx_i == I: gate-interleaved copies that enable the fused FFMA2 step kernel
+ * (h @ W_hh^T + gates in one launch).  Row c' = 96*blk + 32*g + u of the permuted tensors holds original row
+ * g*H + 32*blk + u (g = gate r/z/n); w_hh_perm_dev is additionally K-major: [n_types, H, 3H].  bias_*_perm_dev: [N, 3H] = bias[type(n)] in the same order. */
+int  sd_gru_set_fused(sd_gru* g, const float* w_ih_perm_dev, const float* w_hh_perm_dev,
+                      const float* bias_ih_perm_dev, const float* bias_hh_perm_dev);
 void sd_gru_destroy(sd_gru* g);
 size_t sd_encode_workspace_bytes(int windows, int obs_len, int num_nodes, int hidden, int layers);
 /* obs_dev [W, T, N, F] -> z_dev [W, N, latent] = final_act(fc(h_T)); final_act = SD_ACT_TANH_TANH for

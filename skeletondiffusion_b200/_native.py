@@ -46,6 +46,7 @@ SIGNATURES = {
     "sd_device_supported": (_I, [_I]),
     "sd_glin_create": (_I, [_I, _P, _I, _I, _I, _P, _P, _P, C.POINTER(_P)]),
     "sd_glin_set_bf16": (_I, [_P, _P, _I]),
+    "sd_glin_set_kmajor": (_I, [_P, _P]),
     "sd_glin_destroy": (None, [_P]),
     "sd_glin_forward": (_I, [_P, C.POINTER(SdGlinArgs), _P]),
     "sd_glin_forward_bf16": (_I, [_P, _P, _P, _P, _I, _P, _P, _I, _P, _I, _P]),
@@ -67,6 +68,7 @@ SIGNATURES = {
     "sd_sample_loop": (_I, [_P, _P, _P, C.POINTER(SdView), _P, _P, _I, _I, _P, _I, _P]),
     "sd_fill_normal": (_I, [_P, _I64, _U64, _U64, _P]),
     "sd_gru_create": (_I, [_I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, C.POINTER(_P)]),
+    "sd_gru_set_fused": (_I, [_P, _P, _P, _P, _P]),
     "sd_gru_destroy": (None, [_P]),
     "sd_encode_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I]),
     "sd_encode": (_I, [_P, _P, _I, _P, _P, _I, _I, _I, _P, _I, _P, _I, _P]),

@@ -173,10 +173,10 @@ static int run_glin(const sd_glin* L, GlinCall c, int precision, cudaStream_t st
             if (rc) return rc;
             return node_mix_fp32(L->G, L->N, L->OUT, c.scratch, (long long)L->N * L->OUT, nullptr, c.epi, c.out, c.B, st);
         }
-        return glin_forward_fp32(L->W, L->K, L->OUT, L->types, L->N, L->G, c, st);
+        return glin_forward_fp32(L->W, L->Wt, L->K, L->OUT, L->types, L->N, L->G, c, st);
     }
     if (precision != SD_PREC_FP32) return glin_forward_tc(L, c, precision, st);
-    return glin_forward_fp32(L->W, L->K, L->OUT, L->types, L->N, L->G, c, st);
+    return glin_forward_fp32(L->W, L->Wt, L->K, L->OUT, L->types, L->N, L->G, c, st);
 }
 
 }  // namespace sd
@@ -211,7 +211,7 @@ int sd_glin_create(int num_nodes, const int32_t* node_types_host, int n_types, i
         if (t < 0 || t >= n_types) { delete L; set_error("sd_glin_create: node type %d outside [0,%d)", t, n_types); return SD_ERR_INVALID; }
         L->types.t[n] = (unsigned char)t;
     }
-    L->W = weight_dev; L->bias_node = bias_node_dev; L->G = g_dev; L->W_bf16 = nullptr; L->planes = 0;
+    L->W = weight_dev; L->Wt = nullptr; L->bias_node = bias_node_dev; L->G = g_dev; L->W_bf16 = nullptr; L->planes = 0;
     *out = L;
     return SD_OK;
 }
@@ -219,6 +219,12 @@ int sd_glin_create(int num_nodes, const int32_t* node_types_host, int n_types, i
 int sd_glin_set_bf16(sd_glin* L, const uint16_t* weight_bf16_dev, int planes) {
     if (!L || (planes != 1 && planes != 3)) { set_error("sd_glin_set_bf16: invalid arguments"); return SD_ERR_INVALID; }
     L->W_bf16 = weight_bf16_dev; L->planes = planes;
+    return SD_OK;
+}
+
+int sd_glin_set_kmajor(sd_glin* L, const float* weight_kmajor_dev) {
+    if (!L) { set_error("sd_glin_set_kmajor: null handle"); return SD_ERR_INVALID; }
+    L->Wt = weight_kmajor_dev;
     return SD_OK;
 }
 
@@ -511,7 +517,17 @@ int sd_gru_create(int num_nodes, const int32_t* node_types_host, int n_types, in
         g->types.t[n] = (unsigned char)t;
     }
     g->W_ih = w_ih_dev; g->W_hh = w_hh_dev; g->bias_ih_seq = bias_ih_seq_dev; g->bias_hh_seq = bias_hh_seq_dev; g->gx_seq = gx_seq_dev;
+    g->W_ih_perm = g->W_hh_perm = g->bias_ih_perm = g->bias_hh_perm = nullptr;
     *out = g;
+    return SD_OK;
+}
+
+int sd_gru_set_fused(sd_gru* g, const float* w_ih_perm_dev, const float* w_hh_perm_dev, const float* bias_ih_perm_dev,
+                     const float* bias_hh_perm_dev) {
+    if (!g || !w_ih_perm_dev || !w_hh_perm_dev || !bias_ih_perm_dev || !bias_hh_perm_dev) { set_error("sd_gru_set_fused: null argument"); return SD_ERR_INVALID; }
+    if (g->gx_seq) { set_error("sd_gru_set_fused: only for cells whose graph-influence sequence is the identity"); return SD_ERR_INVALID; }
+    if (g->H % 32) { set_error("sd_gru_set_fused: hidden size must be a multiple of 32"); return SD_ERR_UNSUPPORTED; }
+    g->W_ih_perm = w_ih_perm_dev; g->W_hh_perm = w_hh_perm_dev; g->bias_ih_perm = bias_ih_perm_dev; g->bias_hh_perm = bias_hh_perm_dev;
     return SD_OK;
 }
 
@@ -521,7 +537,7 @@ void sd_gru_destroy(sd_gru* g) { delete g; }
 static int gru_product(const float* W, int K, int OUT, const NodeTypes& types, int N, View a0, View a1, ViewW out, int B, cudaStream_t st) {
     GlinCall c;
     c.a0 = a0; c.a1 = a1; c.row_scale = nullptr; c.epi = no_epilogue(OUT); c.out = out; c.scratch = nullptr; c.B = B;
-    return glin_forward_fp32(W, K, OUT, types, N, nullptr, c, st);
+    return glin_forward_fp32(W, nullptr, K, OUT, types, N, nullptr, c, st);
 }
 
 size_t sd_encode_workspace_bytes(int windows, int obs_len, int num_nodes, int hidden, int layers) {
@@ -564,12 +580,22 @@ int sd_encode(const sd_glin* initial_hidden, sd_gru* const* layers_host, int n_l
         if (!g || g->IN != in_w || g->H != H || g->steps < T) { set_error("sd_encode: GRU layer %d shape/steps mismatch", l); return SD_ERR_INVALID; }
         // x-side products of all frames at once: rows (w, t) -> [W*T, N, 3H]
         View a; a.ptr = seq_in; a.sb = (long long)N * in_w; a.sn = in_w; a.rep = 1; a.width = in_w;
-        rc = gru_product(g->W_ih, in_w, 3 * H, g->types, N, a, null_view(), contiguous_view_w(xr_all, N, 3 * H), W * T, st);
+        const bool fused_cell = g->W_hh_perm != nullptr;
+        rc = gru_product(fused_cell ? g->W_ih_perm : g->W_ih, in_w, 3 * H, g->types, N, a, null_view(), contiguous_view_w(xr_all, N, 3 * H), W * T, st);
         if (rc) return rc;
         for (int t = 0; t < T; ++t) {
             View h_in;
             if (t == 0) h_in = contiguous_view(h0, N, H);
             else { h_in.ptr = seq_out + (size_t)(t - 1) * N * H; h_in.sb = (long long)T * N * H; h_in.sn = H; h_in.rep = 1; h_in.width = H; }
+            if (fused_cell) {   // identity graph influence: h @ W_hh^T and the gates in one FFMA2 kernel, written straight into seq[:, t]
+                View xr; xr.ptr = xr_all + (size_t)t * N * 3 * H; xr.sb = (long long)T * N * 3 * H; xr.sn = 3 * H; xr.rep = 1; xr.width = 3 * H;
+                ViewW h_out; h_out.ptr = seq_out + (size_t)t * N * H; h_out.sb = (long long)T * N * H; h_out.sn = H; h_out.rep = 1; h_out.width = H;
+                if (H == 96 && h_in.rep == 1) rc = gru_step_fused(g->W_hh_perm, H, g->types, N, xr, g->bias_ih_perm, g->bias_hh_perm, h_in, h_out,
+                                                                  nullptr, nullptr, nullptr, 0, W, st);
+                else rc = gru_step_f2(g->W_hh_perm, H, g->types, N, xr, g->bias_ih_perm, g->bias_hh_perm, h_in, h_out, W, st);
+                if (rc) return rc;
+                continue;
+            }
             rc = gru_product(g->W_hh, H, 3 * H, g->types, N, h_in, null_view(), contiguous_view_w(hr, N, 3 * H), W, st);
             if (rc) return rc;
             View xr; xr.ptr = xr_all + (size_t)t * N * 3 * H; xr.sb = (long long)T * N * 3 * H; xr.sn = 3 * H; xr.rep = 1; xr.width = 3 * H;
@@ -628,6 +654,31 @@ int sd_decode(const sd_glin* initial_hidden, const sd_gru* cell, const sd_glin* 
         c.out = contiguous_view_w(h, N, H); c.scratch = scratch; c.B = B;
         rc = run_glin(initial_hidden, c, SD_PREC_FP32, st);
         if (rc) return rc;
+    }
+    if (cell->W_hh_perm && fc->G == nullptr && feat <= 4) {
+        // identity graph influence: one fused FFMA2 kernel per step (h @ W_hh^T + gates) and one tiny output head.
+        // The h state ping-pongs between two buffers (the three 96-column blocks of a row tile read all of h_{i-1}).
+        rc = gru_product(cell->W_ih_perm, cell->IN, 3 * H, cell->types, N, make_view(*x_last), lat, contiguous_view_w(xr_raw, N, 3 * H), B, st);
+        if (rc) return rc;
+        float* h_cur = h;
+        float* h_nxt = hr;      // [bn * 3H] buffer, only bn * H used here
+        for (int i = 0; i < ph; ++i) {
+            ViewW o; o.ptr = out_dev + (size_t)i * N * feat; o.sb = (long long)ph * N * feat; o.sn = feat; o.rep = 1; o.width = feat;
+            if (H == 96 && feat <= 3) {   // one launch per step: products, gates and the output head
+                rc = gru_step_fused(cell->W_hh_perm, H, cell->types, N, contiguous_view(xr_raw, N, 3 * H), cell->bias_ih_perm,
+                                    cell->bias_hh_perm, contiguous_view(h_cur, N, H), contiguous_view_w(h_nxt, N, H), fc->W, fc->bias_node,
+                                    &o, feat, B, st);
+                if (rc) return rc;
+            } else {
+                rc = gru_step_f2(cell->W_hh_perm, H, cell->types, N, contiguous_view(xr_raw, N, 3 * H), cell->bias_ih_perm, cell->bias_hh_perm,
+                                 contiguous_view(h_cur, N, H), contiguous_view_w(h_nxt, N, H), B, st);
+                if (rc) return rc;
+                rc = gru_out_fc_fp32(fc->W, fc->bias_node, fc->types, N, H, feat, h_nxt, o, SD_ACT_TANH, B, st);
+                if (rc) return rc;
+            }
+            float* t = h_cur; h_cur = h_nxt; h_nxt = t;
+        }
+        return SD_OK;
     }
     // loop-invariant x-side product of rec_input = cat[x_{-1}, latent]   (decoder.py:81,93)
     rc = gru_product(cell->W_ih, cell->IN, 3 * H, cell->types, N, make_view(*x_last), lat, contiguous_view_w(xr_raw, N, 3 * H), B, st);

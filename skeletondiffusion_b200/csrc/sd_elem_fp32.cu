@@ -308,6 +308,48 @@ int gru_gates_fp32(const View& xr, const float* xr_bias, const float* hr, const 
 }
 
 // =============================================================================================
+// decoder output head with identity graph influence: y[b,n,:] = act(W_fc[type(n)] h[b,n,:] + bias[n])  (decoder.py:97-98)
+// F <= 4 outputs per node, one warp per (sample, node) row, shuffle reduction.
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+gru_out_fc_kernel(const float* __restrict__ Wfc, const float* __restrict__ bias_node, const NodeTypes types, int N, int H, int F,
+                  const float* __restrict__ h, const ViewW out, int act, long long rows) {
+    const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const int n = (int)(r % N), b = (int)(r / N);
+    const float* hr = h + r * H;
+    const float* w = Wfc + (long long)types.t[n] * F * H;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int u = lane; u < H; u += 32) {
+        const float hv = __ldg(hr + u);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) if (c < F) acc[c] = fmaf(__ldg(w + c * H + u), hv, acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+    if (lane < F) {
+        float v = acc[0];
+        if (lane == 1) v = acc[1]; else if (lane == 2) v = acc[2]; else if (lane == 3) v = acc[3];
+        if (bias_node) v += __ldg(bias_node + (long long)n * F + lane);
+        if (act == SD_ACT_TANH) v = tanhf(v);
+        row_ptr(out, b, n)[lane] = v;
+    }
+}
+
+int gru_out_fc_fp32(const float* Wfc, const float* bias_node, const NodeTypes& types, int N, int H, int F, const float* h,
+                    const ViewW& out, int act, int B, cudaStream_t st) {
+    if (B <= 0) return SD_OK;
+    if (F > 4) { set_error("gru_out_fc: feature size %d > 4", F); return SD_ERR_UNSUPPORTED; }
+    const long long rows = (long long)B * N;
+    gru_out_fc_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(Wfc, bias_node, types, N, H, F, h, out, act, rows);
+    SD_LAUNCH_OK("gru_out_fc_kernel");
+    return SD_OK;
+}
+
+// =============================================================================================
 // time conditioning table: sinusoidal embedding -> Linear -> GELU(erf) -> Linear -> per block
 // Tanh -> Linear   (nn/generator.py:47-55; layers/attention.py:81-84).  Batch-invariant: one row per
 // distinct time value, computed once per plan.

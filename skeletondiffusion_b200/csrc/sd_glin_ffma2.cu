@@ -1,0 +1,296 @@
+// Grouped (per-node-type) fp32 GEMM on the packed FFMA2 pipe (fma.rn.f32x2: two fp32 FMAs per lane per
+// instruction — the only way to reach the B200 FP32 peak) with the graph-linear epilogue or a fused GRU-cell
+// epilogue.  Exact fp32 (same arithmetic as the reference up to summation order): this is the <=1e-4 parity path
+// for shapes with OUT % 96 == 0 and K % 32 == 0 (all Denoiser layers, the GRU hidden products).
+//
+//   tile 128 samples x 96 outputs x 32 k, 256 threads, 8 x 6 outputs per thread held as 24 float2 accumulators.
+//   Operands stream through a 3-stage cp.async (LDGSTS) ring: A rows as stored ([row][32 k], 16-byte chunks
+//   XOR-swizzled by row), weights from a K-major copy ([k][96 outputs]) so that an output PAIR is one LDS.64.
+//   Per 4 k: 8 x LDS.128 (A, broadcast inside a half-warp) + 12 x LDS.64 (B pairs) feed 96 FFMA2 whose scalar
+//   A operand is broadcast by the instruction itself (SASS: FFMA2 Rd, Ra.F32, Rb.F32x2.HI_LO, Rd).
+//
+// Reference: GraphLinear.forward (graph_structural.py:30-43); StaticGraphGRUCell_.forward (recurrent.py:333-358).
+#include "sd_internal.h"
+#include <cuda_pipeline_primitives.h>
+
+namespace sd {
+
+constexpr int F2_BM = 128, F2_BN = 96, F2_BK = 32, F2_THREADS = 256, F2_STAGES = 3;
+constexpr int F2_A_BYTES = F2_BM * F2_BK * 4;       // 16 KB
+constexpr int F2_B_BYTES = F2_BK * F2_BN * 4;       // 12 KB
+constexpr int F2_SMEM = F2_STAGES * (F2_A_BYTES + F2_B_BYTES);
+
+__device__ __forceinline__ void ffma2(float2& d, float a, float2 b) {
+    unsigned long long dd = *reinterpret_cast<unsigned long long*>(&d), bb = *reinterpret_cast<unsigned long long*>(&b), aa;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dd) : "l"(aa), "l"(bb));
+    d = *reinterpret_cast<float2*>(&dd);
+}
+
+struct F2Params {
+    View a0, a1;
+    const float* Wt;           // K-major weights [types][K][OUT]
+    int K, OUT, N, B;
+    NodeTypes types;
+    const float* row_scale;
+    Epilogue epi;
+    ViewW out;
+    int fused;
+    // GRU mode (columns of every 96-block ordered [r | z | n] x 32 units):
+    View xr;                   // x-side product, same permuted column order, [.., 3H]
+    const float* bias_x;       // [N][3H] permuted
+    const float* bias_h;       // [N][3H] permuted
+    View h_prev; ViewW h_out;  // [.., H]
+    int H;
+};
+
+template <bool GRU>
+__global__ void __launch_bounds__(F2_THREADS, 2)
+glin_gemm_f2_kernel(const F2Params p) {
+    extern __shared__ __align__(128) uint8_t f2_smem[];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int node = blockIdx.y, b0 = blockIdx.x * F2_BM, o0 = blockIdx.z * F2_BN;
+    const float* Wt = p.Wt + (long long)p.types.t[node] * p.K * p.OUT + o0;
+
+    // cp.async sources: A chunk f = tid + 256 i -> (row = f % 128, c4 = f / 128); W chunk f -> (k = f / 24, c4 = f % 24)
+    const int a_row = tid & 127, a_c4 = tid >> 7;
+    const bool a_ok = b0 + a_row < p.B;
+    const float* ar0 = a_ok ? row_ptr(p.a0, b0 + a_row, node) : nullptr;
+    const float* ar1 = (a_ok && p.a1.ptr) ? row_ptr(p.a1, b0 + a_row, node) : nullptr;
+    const int nk = p.K / F2_BK;
+    auto issue = [&](int kt) {
+        if (kt < nk) {
+            uint8_t* As = f2_smem + (kt % F2_STAGES) * (F2_A_BYTES + F2_B_BYTES);
+            uint8_t* Bs = As + F2_A_BYTES;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int c4 = a_c4 + 2 * i;
+                const int k = kt * F2_BK + c4 * 4;
+                void* dst = As + a_row * 128 + ((c4 ^ (a_row & 7)) << 4);
+                const float* src = nullptr;
+                if (a_ok) src = (k < p.a0.width) ? ar0 + k : (ar1 ? ar1 + (k - p.a0.width) : nullptr);
+                if (src) __pipeline_memcpy_async(dst, src, 16);
+                else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const int f = tid + 256 * i, k = f / 24, c4 = f % 24;
+                __pipeline_memcpy_async(Bs + k * (F2_BN * 4) + c4 * 16, Wt + (long long)(kt * F2_BK + k) * p.OUT + c4 * 4, 16);
+            }
+        }
+        __pipeline_commit();
+    };
+
+    float2 acc[8][3];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc[i][j] = make_float2(0.f, 0.f);
+
+    issue(0);
+    issue(1);
+    for (int kt = 0; kt < nk; ++kt) {
+        issue(kt + 2);
+        __pipeline_wait_prior(2);        // tile kt has landed (two younger groups may be in flight)
+        __syncthreads();
+        const uint8_t* As = f2_smem + (kt % F2_STAGES) * (F2_A_BYTES + F2_B_BYTES);
+        const float* Bs = reinterpret_cast<const float*>(As + F2_A_BYTES);
+#pragma unroll
+        for (int k4 = 0; k4 < F2_BK / 4; ++k4) {
+            float4 a[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = ty * 8 + i;
+                a[i] = *reinterpret_cast<const float4*>(As + r * 128 + ((k4 ^ (r & 7)) << 4));
+            }
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                float2 b[3];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) b[j] = *reinterpret_cast<const float2*>(Bs + (k4 * 4 + kk) * F2_BN + 2 * tx + 32 * j);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float av = kk == 0 ? a[i].x : (kk == 1 ? a[i].y : (kk == 2 ? a[i].z : a[i].w));
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) ffma2(acc[i][j], av, b[j]);
+                }
+            }
+        }
+        __syncthreads();                 // stage kt % 3 is refilled by issue(kt + 3) in the next iteration
+    }
+
+    // Epilogues: every global load of a 4-row group (residual / x-side gates / previous state) is issued before its
+    // first use.  A first version loaded per element inside the activation chain and spent 63 % of the kernel's
+    // stall samples waiting on those loads one at a time.
+    if (!GRU) {
+        if (!p.fused) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int b = b0 + ty * 8 + i;
+                if (b >= p.B) continue;
+                float* orow = row_ptr(p.out, b, node) + o0 + 2 * tx;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) *reinterpret_cast<float2*>(orow + 32 * j) = acc[i][j];
+            }
+            return;
+        }
+        const Epilogue& e = p.epi;
+        const bool per_sample_ss = e.ss && e.ss_row_idx;
+        float2 mul[3], add[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int c = o0 + 2 * tx + 32 * j;
+            const float2 bias = e.bias_node ? __ldg(reinterpret_cast<const float2*>(e.bias_node + (long long)node * e.OUT + c)) : make_float2(0.f, 0.f);
+            mul[j] = make_float2(1.f, 1.f);
+            add[j] = bias;
+            if (e.ss && !per_sample_ss) {
+                const float* row = e.ss + (long long)e.ss_row * e.ss_stride;
+                const float2 sc = __ldg(reinterpret_cast<const float2*>(row + c)), sh = __ldg(reinterpret_cast<const float2*>(row + e.OUT + c));
+                mul[j] = make_float2(sc.x + 1.f, sc.y + 1.f);
+                add[j] = make_float2(fmaf(bias.x, mul[j].x, sh.x), fmaf(bias.y, mul[j].y, sh.y));
+            }
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float2 res[4][3];
+            float rs[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int b = b0 + ty * 8 + half * 4 + i;
+                const bool ok = b < p.B;
+                rs[i] = (ok && p.row_scale) ? __ldg(p.row_scale + (long long)b * p.N + node) : 1.0f;
+                const float* rrow = (ok && e.residual.ptr) ? row_ptr(e.residual, b, node) + o0 + 2 * tx : nullptr;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) res[i][j] = rrow ? __ldg(reinterpret_cast<const float2*>(rrow + 32 * j)) : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int b = b0 + ty * 8 + half * 4 + i;
+                if (b >= p.B) continue;
+                float* orow = row_ptr(p.out, b, node) + o0 + 2 * tx;
+                float2 m2[3], a2[3];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) { m2[j] = mul[j]; a2[j] = add[j]; }
+                if (per_sample_ss) {       // training-loss entry point: one time row per sample
+                    const float* row = e.ss + (long long)__ldg(e.ss_row_idx + b) * e.ss_stride;
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const int c = o0 + 2 * tx + 32 * j;
+                        const float2 sc = __ldg(reinterpret_cast<const float2*>(row + c)), sh = __ldg(reinterpret_cast<const float2*>(row + e.OUT + c));
+                        m2[j] = make_float2(sc.x + 1.f, sc.y + 1.f);
+                        a2[j] = make_float2(fmaf(add[j].x, m2[j].x, sh.x), fmaf(add[j].y, m2[j].y, sh.y));
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    float2 v;
+                    v.x = fmaf(acc[half * 4 + i][j].x * rs[i], m2[j].x, a2[j].x);
+                    v.y = fmaf(acc[half * 4 + i][j].y * rs[i], m2[j].y, a2[j].y);
+                    if (e.act == SD_ACT_TANH) { v.x = tanhf(v.x); v.y = tanhf(v.y); }
+                    else if (e.act == SD_ACT_TANH_TANH) { v.x = tanhf(tanhf(v.x)); v.y = tanhf(tanhf(v.y)); }
+                    v.x += res[i][j].x; v.y += res[i][j].y;
+                    *reinterpret_cast<float2*>(orow + 32 * j) = v;
+                }
+            }
+        }
+    } else {
+        // fused GRU cell (recurrent.py:351-358): this 96-column block holds gates r|z|n of units u0 .. u0+31
+        const int u0 = blockIdx.z * 32 + 2 * tx;
+        const float* bx = p.bias_x + (long long)node * 3 * p.H + o0;
+        const float* bh = p.bias_h + (long long)node * 3 * p.H + o0;
+        float2 bxg[3], bhg[3];
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+            bxg[g] = __ldg(reinterpret_cast<const float2*>(bx + 32 * g + 2 * tx));
+            bhg[g] = __ldg(reinterpret_cast<const float2*>(bh + 32 * g + 2 * tx));
+        }
+        auto cell = [](float ir, float iz, float in_, float hr, float hz, float hn, float hprev) {
+            const float r = 1.0f / (1.0f + expf(-(ir + hr)));
+            const float z = 1.0f / (1.0f + expf(-(iz + hz)));
+            const float n = tanhf(in_ + r * hn);
+            return n - n * z + z * hprev;
+        };
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float2 xg[4][3], hp[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int b = b0 + ty * 8 + half * 4 + i;
+                const bool ok = b < p.B;
+                const float* xrow = ok ? row_ptr(p.xr, b, node) + o0 + 2 * tx : nullptr;
+#pragma unroll
+                for (int g = 0; g < 3; ++g) xg[i][g] = ok ? __ldg(reinterpret_cast<const float2*>(xrow + 32 * g)) : make_float2(0.f, 0.f);
+                hp[i] = ok ? __ldg(reinterpret_cast<const float2*>(row_ptr(p.h_prev, b, node) + u0)) : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int b = b0 + ty * 8 + half * 4 + i;
+                if (b >= p.B) continue;
+                const float2* ac = acc[half * 4 + i];
+                float2 hy;
+                hy.x = cell(xg[i][0].x + bxg[0].x, xg[i][1].x + bxg[1].x, xg[i][2].x + bxg[2].x, ac[0].x + bhg[0].x, ac[1].x + bhg[1].x,
+                            ac[2].x + bhg[2].x, hp[i].x);
+                hy.y = cell(xg[i][0].y + bxg[0].y, xg[i][1].y + bxg[1].y, xg[i][2].y + bxg[2].y, ac[0].y + bhg[0].y, ac[1].y + bhg[1].y,
+                            ac[2].y + bhg[2].y, hp[i].y);
+                *reinterpret_cast<float2*>(row_ptr(p.h_out, b, node) + u0) = hy;
+            }
+        }
+    }
+}
+
+static inline bool al16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
+static inline bool view16(const View& v) { return v.ptr == nullptr || (al16(v.ptr) && v.sb % 4 == 0 && v.sn % 4 == 0); }
+
+bool glin_f2_supported(const View& a0, const View& a1, int K, int OUT, const float* Wt, const ViewW& out) {
+    const int k0 = a0.width, k1 = a1.ptr ? a1.width : 0;
+    if (Wt == nullptr || k0 + k1 != K || K % F2_BK || OUT % F2_BN) return false;
+    if (k0 % 4 || k1 % 4) return false;     // a 16-byte chunk never straddles the segment boundary
+    if (!view16(a0) || !view16(a1) || !al16(Wt)) return false;
+    if (((reinterpret_cast<uintptr_t>(out.ptr) & 7u) != 0) || out.sb % 2 || out.sn % 2) return false;
+    return true;
+}
+
+template <bool GRU>
+static int f2_launch(const F2Params& p, cudaStream_t st) {
+    auto kern = glin_gemm_f2_kernel<GRU>;
+    static bool configured = false;
+    if (!configured) {
+        SD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
+        configured = true;
+    }
+    dim3 grid((p.B + F2_BM - 1) / F2_BM, p.N, p.OUT / F2_BN);
+    kern<<<grid, F2_THREADS, F2_SMEM, st>>>(p);
+    SD_LAUNCH_OK("glin_gemm_f2_kernel");
+    return SD_OK;
+}
+
+int glin_f2_launch(const float* Wt, int K, int OUT, const NodeTypes& types, int N, const GlinCall& c, const ViewW& out, bool fused, cudaStream_t st) {
+    F2Params p;
+    p.a0 = c.a0; p.a1 = c.a1; p.Wt = Wt; p.K = K; p.OUT = OUT; p.N = N; p.B = c.B; p.types = types;
+    p.row_scale = c.row_scale; p.epi = c.epi; p.epi.OUT = OUT; p.out = out; p.fused = fused ? 1 : 0;
+    p.bias_x = p.bias_h = nullptr; p.H = 0;
+    return f2_launch<false>(p, st);
+}
+
+// h_out = GRUCell(xr (+bias_x), h_prev @ W_hh^T (+bias_h), h_prev) with identity graph influence.  W_hh is given K-major
+// with gate-interleaved columns ([types][H][3H], every 96-column block = [r | z | n] of 32 consecutive units); biases and xr
+// columns use the same order.
+int gru_step_f2(const float* W_hh_perm_t, int H, const NodeTypes& types, int N, const View& xr, const float* bias_x, const float* bias_h,
+                const View& h_prev, const ViewW& h_out, int B, cudaStream_t st) {
+    if (B <= 0) return SD_OK;
+    if (H % 32 || (3 * H) % F2_BN || !view16(h_prev) || !view16(xr) || !al16(W_hh_perm_t) || h_prev.width != H) {
+        set_error("gru_step_f2: unsupported shape H=%d", H);
+        return SD_ERR_UNSUPPORTED;
+    }
+    F2Params p;
+    p.a0 = h_prev; p.a1.ptr = nullptr; p.a1.sb = p.a1.sn = 0; p.a1.rep = 1; p.a1.width = 0;
+    p.Wt = W_hh_perm_t; p.K = H; p.OUT = 3 * H; p.N = N; p.B = B; p.types = types;
+    p.row_scale = nullptr; p.fused = 0;
+    p.epi.bias_node = nullptr; p.epi.ss = nullptr; p.epi.ss_row_idx = nullptr; p.epi.ss_row = 0; p.epi.ss_stride = 0; p.epi.act = 0;
+    p.epi.residual.ptr = nullptr; p.epi.OUT = 3 * H;
+    p.out = h_out;
+    p.xr = xr; p.bias_x = bias_x; p.bias_h = bias_h; p.h_prev = h_prev; p.h_out = h_out; p.H = H;
+    return f2_launch<true>(p, st);
+}
+
+}  // namespace sd

@@ -248,12 +248,22 @@ int node_mix_fp32(const float* G, int N, int OUT, const float* y, long long y_sb
     return SD_OK;
 }
 
-int glin_forward_fp32(const float* W, int K, int OUT, const NodeTypes& types, int N,
+int glin_forward_fp32(const float* W, const float* Wt, int K, int OUT, const NodeTypes& types, int N,
                       const float* G, const GlinCall& c, cudaStream_t st) {
     if (c.B <= 0) return SD_OK;
     const int kin = c.a0.width + (c.a1.ptr ? c.a1.width : 0);
     if (kin != K) { set_error("glin: input width %d != in_features %d", kin, K); return SD_ERR_INVALID; }
     if (G != nullptr && c.scratch == nullptr) { set_error("glin: scratch required for non-identity G"); return SD_ERR_INVALID; }
+    {   // FFMA2 kernel for the regular shapes (sd_glin_ffma2.cu); the generic kernel below handles ragged K / OUT
+        const bool fused = (G == nullptr);
+        const ViewW dst = fused ? c.out : contiguous_view_w(c.scratch, N, OUT);
+        if (glin_f2_supported(c.a0, c.a1, K, OUT, Wt, dst) && c.out.rep == 1) {
+            int rc = glin_f2_launch(Wt, K, OUT, types, N, c, dst, fused, st);
+            if (rc || fused) return rc;
+            Epilogue e = c.epi; e.OUT = OUT;
+            return node_mix_fp32(G, N, OUT, c.scratch, (long long)N * OUT, c.row_scale, e, c.out, c.B, st);
+        }
+    }
     GemmParams p;
     p.a0 = c.a0; p.a1 = c.a1; p.W = W; p.K = K; p.OUT = OUT; p.N = N; p.B = c.B; p.types = types;
     p.row_scale = c.row_scale; p.epi = c.epi; p.epi.OUT = OUT;

@@ -24,8 +24,9 @@ using namespace sd::tc;
 
 constexpr int T3_BM = 128, T3_BK = 64;
 constexpr int T3_PRODUCERS = 256;   // warps 0-7 (two per scheduler hide each other's LDG latency)
-constexpr int T3_MMA_WARP = 8, T3_ALLOC_WARP = 9, T3_EPI_WARP0 = 12;
-constexpr int T3_THREADS = 512;     // 16 warps x 128 registers
+constexpr int T3_EPI_WARP0 = 8;     // warps 8-11: epilogue (warp % 4 = TMEM lane quarter)
+constexpr int T3_MMA_WARP = 12, T3_ALLOC_WARP = 12;   // warp 12: TMEM allocation, weight TMA, MMA issue
+constexpr int T3_THREADS = 416;     // 13 warps (register file is allocated as for 16: 128 registers per thread)
 constexpr int T3_MAX_STAGES = 4;
 constexpr int T3_STAGE_BYTES = 3 * T3_BM * 128;    // three plane tiles of 128 rows x 128 B
 
@@ -98,37 +99,48 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
         const int col4 = t & 15;            // which float4 of the 64-wide k-block row
         const int row0 = t >> 4;            // rows row0 + 16*i, i = 0..7
         const uint32_t chunk = (uint32_t)(col4 >> 1), half = (uint32_t)(col4 & 1) << 3;
+        // Registers are the only place where loads can be "in flight" here (shared memory is full of weight and
+        // plane tiles): the producers double-buffer 8 x float4 granules, so the next k-block's loads are outstanding
+        // while the current one is split and stored (a 3-deep pipeline does not fit the 128-register budget).
         int stage = 0; uint32_t phase = 0;
-        for (long long it = item_lo; it < item_hi; ++it) {
-            const long long g = it / p.MT;
-            const int mt = (int)(it % p.MT);
-            const int node = (int)(g / p.NT);
-            for (int kb = 0; kb < p.KB; ++kb) {
-                const View& seg = kb < KB0 ? p.a0 : p.a1;
-                const int koff = (kb < KB0 ? kb : kb - KB0) * T3_BK + col4 * 4;
-                float4 v[8];
+        const long long q_end = (item_hi - item_lo) * p.KB;       // flattened (tile, k-block) sequence
+        auto fetch = [&](long long q, float4 (&v)[8]) {
+            if (q >= q_end) return;
+            const long long it = item_lo + q / p.KB;
+            const int kb = (int)(q % p.KB);
+            const int mt = (int)(it % p.MT), node = (int)((it / p.MT) / p.NT);
+            const View& seg = kb < KB0 ? p.a0 : p.a1;
+            const int koff = (kb < KB0 ? kb : kb - KB0) * T3_BK + col4 * 4;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int b = mt * T3_BM + row0 + 16 * i;
-                    v[i] = (b < p.B) ? __ldg(reinterpret_cast<const float4*>(row_ptr(seg, b, node) + koff)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                mbar_wait(&bars->empty[stage], phase ^ 1);
-                uint8_t* st = a_smem + (size_t)stage * T3_STAGE_BYTES;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = row0 + 16 * i;
-                    uint32_t h[4], m[4], l[4];
-                    split3(v[i].x, h[0], m[0], l[0]); split3(v[i].y, h[1], m[1], l[1]);
-                    split3(v[i].z, h[2], m[2], l[2]); split3(v[i].w, h[3], m[3], l[3]);
-                    const uint32_t off = (uint32_t)r * 128u + ((chunk ^ (uint32_t)(r & 7)) << 4) + half;
-                    *reinterpret_cast<uint2*>(st + off) = make_uint2(pack_hi(h[0], h[1]), pack_hi(h[2], h[3]));
-                    *reinterpret_cast<uint2*>(st + T3_BM * 128 + off) = make_uint2(pack_hi(m[0], m[1]), pack_hi(m[2], m[3]));
-                    *reinterpret_cast<uint2*>(st + 2 * T3_BM * 128 + off) = make_uint2(pack_hi(l[0], l[1]), pack_hi(l[2], l[3]));
-                }
-                fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
-                mbar_arrive(&bars->full[stage]);
-                if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+            for (int i = 0; i < 8; ++i) {
+                const int b = mt * T3_BM + row0 + 16 * i;
+                v[i] = (b < p.B) ? __ldg(reinterpret_cast<const float4*>(row_ptr(seg, b, node) + koff)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+        };
+        auto emit = [&](long long q, const float4 (&v)[8]) {
+            if (q >= q_end) return;
+            mbar_wait(&bars->empty[stage], phase ^ 1);
+            uint8_t* st = a_smem + (size_t)stage * T3_STAGE_BYTES;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = row0 + 16 * i;
+                uint32_t h[4], m[4], l[4];
+                split3(v[i].x, h[0], m[0], l[0]); split3(v[i].y, h[1], m[1], l[1]);
+                split3(v[i].z, h[2], m[2], l[2]); split3(v[i].w, h[3], m[3], l[3]);
+                const uint32_t off = (uint32_t)r * 128u + ((chunk ^ (uint32_t)(r & 7)) << 4) + half;
+                *reinterpret_cast<uint2*>(st + off) = make_uint2(pack_hi(h[0], h[1]), pack_hi(h[2], h[3]));
+                *reinterpret_cast<uint2*>(st + T3_BM * 128 + off) = make_uint2(pack_hi(m[0], m[1]), pack_hi(m[2], m[3]));
+                *reinterpret_cast<uint2*>(st + 2 * T3_BM * 128 + off) = make_uint2(pack_hi(l[0], l[1]), pack_hi(l[2], l[3]));
+            }
+            fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            mbar_arrive(&bars->full[stage]);
+            if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+        };
+        float4 va[8], vb[8];
+        fetch(0, va);
+        for (long long q = 0; q < q_end; q += 2) {
+            fetch(q + 1, vb); emit(q, va);
+            fetch(q + 2, va); emit(q + 1, vb);
         }
     } else if (warp == T3_MMA_WARP) {
         // ================================================================ weight TMA + MMA issue
@@ -183,8 +195,8 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
             }
         }
         __syncwarp();
-    } else if (warp >= T3_EPI_WARP0) {
-        // ================================================================ epilogue (warps 12-15: warp % 4 = lane quarter)
+    } else if (warp >= T3_EPI_WARP0 && warp < T3_EPI_WARP0 + 4) {
+        // ================================================================ epilogue (warps 8-11: warp % 4 = lane quarter)
         const int quarter = warp & 3;
         const int et = threadIdx.x - T3_EPI_WARP0 * 32;
         uint32_t acc = 0, acc_phase = 0;

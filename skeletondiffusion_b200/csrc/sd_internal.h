@@ -7,6 +7,7 @@ struct sd_glin {
     int N, n_types, K, OUT;
     sd::NodeTypes types;
     const float* W;          // [n_types][OUT][K]
+    const float* Wt;         // K-major copy [n_types][K][OUT] for the FFMA2 kernel, or null
     const float* bias_node;  // [N][OUT] or null
     const float* G;          // [N][N] or null (identity)
     const uint16_t* W_bf16;  // [planes][n_types][OUT][K] or null
@@ -21,6 +22,12 @@ struct sd_gru {
     const float* bias_ih_seq;  // [steps][N][3H]
     const float* bias_hh_seq;  // [steps][N][3H]
     const float* gx_seq;     // [steps][N][N] or null
+    // gate-interleaved copies for the fused FFMA2 GRU step (identity graph influence only); row c' = 96*blk + 32*g + u
+    // holds original row g*H + 32*blk + u, so every 96-column GEMM block carries gates r|z|n of 32 units
+    const float* W_ih_perm;  // [n_types][3H][IN]
+    const float* W_hh_perm;  // K-major: [n_types][H][3H]
+    const float* bias_ih_perm;  // [N][3H]
+    const float* bias_hh_perm;  // [N][3H]
 };
 
 struct sd_diffusion {
@@ -48,7 +55,7 @@ struct GlinCall {
     float* scratch;   // needed iff G != null
     int B;
 };
-int glin_forward_fp32(const float* W, int K, int OUT, const NodeTypes& types, int N,
+int glin_forward_fp32(const float* W, const float* Wt, int K, int OUT, const NodeTypes& types, int N,
                       const float* G, const GlinCall& c, cudaStream_t st);
 int node_mix_fp32(const float* G, int N, int OUT, const float* y, long long y_sb, const float* row_scale,
                   const Epilogue& epi, const ViewW& out, int B, cudaStream_t st);
@@ -77,6 +84,14 @@ struct TcCall {
     int B;
     int accurate_tanh;
 };
+bool glin_f2_supported(const View& a0, const View& a1, int K, int OUT, const float* Wt, const ViewW& out);
+int glin_f2_launch(const float* Wt, int K, int OUT, const NodeTypes& types, int N, const GlinCall& c, const ViewW& out, bool fused, cudaStream_t st);
+int gru_step_f2(const float* W_hh_perm_t, int H, const NodeTypes& types, int N, const View& xr, const float* bias_x, const float* bias_h,
+                const View& h_prev, const ViewW& h_out, int B, cudaStream_t st);
+int gru_step_fused(const float* W_hh_perm_t, int H, const NodeTypes& types, int N, const View& xr, const float* bias_x, const float* bias_h,
+                   const View& h_prev, const ViewW& h_out, const float* Wfc, const float* bias_fc, const ViewW* y, int F, int B, cudaStream_t st);
+int gru_out_fc_fp32(const float* Wfc, const float* bias_node, const NodeTypes& types, int N, int H, int F, const float* h,
+                    const ViewW& out, int act, int B, cudaStream_t st);
 bool glin_tc3_supported(int K0, int K1, int OUT);
 int glin_tc3_launch(const sd_glin* L, const GlinCall& c, const ViewW& out, bool apply_epilogue, cudaStream_t st);
 bool glin_tc_supported(int K0, int K1, int OUT);

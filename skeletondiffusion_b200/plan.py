@@ -71,6 +71,11 @@ class GlinPlan:
         nv.check(nv.load().sd_glin_create(num_nodes, self.types_host, self.n_types, self.in_features, self.out_features,
                                           self.weight.data_ptr(), nv.dptr(self.bias_node), nv.dptr(self.g),
                                           C.byref(self.handle)), "sd_glin_create")
+        # K-major fp32 copy for the FFMA2 kernel (an output pair is then one 8-byte shared-memory load)
+        self.weight_kmajor = None
+        if self.out_features % 96 == 0 and self.in_features % 32 == 0:
+            self.weight_kmajor = self.weight.transpose(1, 2).contiguous()
+            nv.check(nv.load().sd_glin_set_kmajor(self.handle, self.weight_kmajor.data_ptr()), "sd_glin_set_kmajor")
         # bf16 weight planes for the tcgen05 paths (K-major [3, types, out, in], read by TMA): w = p0 + p1 + p2 exactly;
         # plane 0 alone (= bf16(w)) is what the plain bf16 path multiplies with
         p0 = self.weight.to(torch.bfloat16)
@@ -282,6 +287,18 @@ class GruPlan:
         nv.check(nv.load().sd_gru_create(N, self.types_host, self.w_ih.shape[0], cell.input_size, H, self.w_ih.data_ptr(),
                                          self.w_hh.data_ptr(), self.bias_ih_seq.data_ptr(), self.bias_hh_seq.data_ptr(),
                                          nv.dptr(self.gx_seq), steps, C.byref(self.handle)), "sd_gru_create")
+        if self.identity and H % 32 == 0:
+            # gate-interleaved copies for the fused FFMA2 GRU step: every 96-row block = gates r|z|n of 32 units
+            blk = torch.arange(H // 32, device=dev).view(-1, 1, 1)
+            g = torch.arange(3, device=dev).view(1, -1, 1)
+            u = torch.arange(32, device=dev).view(1, 1, -1)
+            perm = (g * H + 32 * blk + u).reshape(-1)                       # new row -> original row
+            self.w_ih_perm = self.w_ih[:, perm].contiguous()
+            self.w_hh_perm = self.w_hh[:, perm].transpose(1, 2).contiguous()     # K-major [types, H, 3H]
+            self.bias_ih_perm = b_ih[:, perm].contiguous()
+            self.bias_hh_perm = b_hh[:, perm].contiguous()
+            nv.check(nv.load().sd_gru_set_fused(self.handle, self.w_ih_perm.data_ptr(), self.w_hh_perm.data_ptr(),
+                                                self.bias_ih_perm.data_ptr(), self.bias_hh_perm.data_ptr()), "sd_gru_set_fused")
 
     def __del__(self):
         try:

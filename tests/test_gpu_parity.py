@@ -234,6 +234,37 @@ def test_step_kernel_linearity_full_size(cuda_device):
     assert G.rel_err(s3.cpu(), (2.0 * s1 - 0.5 * s2).cpu()) < 1e-5
 
 
+@pytest.mark.parametrize("dataset", ["amass", "h36m"])
+def test_autoencoder_identity_influence_fast_path(cuda_device, dataset):
+    """Identity graph influence (the reference initialisation) selects the fused FFMA2 GRU step; the weights are still
+    the dense per-type stress weights, so a wrong gate interleave or type index cannot hide."""
+    import skeletondiffusion_b200 as sdb
+    from skeletondiffusion_b200.testing import synth_state_dict
+    spec = sdb.get_skeleton(dataset)
+    ae, _ = sdb.build_models(spec, "cpu", seed=3)
+    sd = synth_state_dict(ae.state_dict(), seed=77, mode="perturbed", gain=2.5)
+    N = spec.num_nodes
+    for k in sd:
+        if k.endswith(".G"):
+            sd[k] = torch.eye(N)
+        if k.endswith(".G_add"):
+            sd[k] = torch.zeros(N, N)
+    ae.load_state_dict(sd)
+    cfg = G.dataset_cfg(spec)
+    g = torch.Generator().manual_seed(5)
+    W, S, ph = 3, 4, 17
+    obs = (torch.randn(W, spec.obs_length, N, 3, generator=g) * 0.3).clamp(-1, 1)
+    lat = torch.tanh(torch.randn(W * S, N, 96, generator=g))
+    z_ref = oc.encode(sd, cfg, obs)
+    p_ref = oc.decode(sd, cfg, obs[:, -2:].repeat_interleave(S, 0), lat, ph)
+    ae = ae.to(cuda_device).eval()
+    assert ae.decoder.rnn.layers[0].plan(ph).identity
+    z = ae.get_past_embedding(obs.to(cuda_device))
+    p = ae.decode(obs.to(cuda_device), lat.to(cuda_device), None, ph=ph)
+    assert G.rel_err(z.cpu(), z_ref) < FP32_TOL
+    assert G.rel_err(p.cpu(), p_ref) < FP32_TOL
+
+
 def test_cpu_tensor_is_rejected(cuda_device):
     import skeletondiffusion_b200 as sdb
     nv = _native()
