@@ -1,7 +1,11 @@
 // Node attention: softmax_j(q_n . k_j * dh^-1/2) v_j over the nodes of one sample, one head.
 // Reference: Attention.forward, src/core/network/layers/attention.py:125-135.
-// One warp per (sample, head); lane = query node; K/V of the head live in shared memory (fp32);
-// the qkv / out tensors are fp32 (parity path) or bf16 (tensor-core path), math is always fp32.
+//
+// One warp per (sample, head) task, several tasks per warp (grid-stride), lane = query node.  The head's Q/K/V rows
+// ([N, dh] each) are copied into shared memory with coalesced 16-byte loads (rows padded to dh + 4 floats so that a
+// lane reading ITS OWN q row is bank-conflict free; K/V rows are read as warp-wide broadcasts).  All products run
+// on the packed FFMA2 pipe: q.k as float2 partial sums over channel pairs, p_j * v_j as scalar x float2.
+// qkv / out are fp32 (parity path) or bf16 (tensor-core path); the math is fp32 in both.
 #include "sd_internal.h"
 #include <math.h>
 
@@ -9,110 +13,145 @@ namespace sd {
 
 template <typename T> struct Io;
 template <> struct Io<float> {
-    static __device__ __forceinline__ void load4(const float* p, float (&v)[4]) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-    }
-    static __device__ __forceinline__ void store4(float* p, const float (&v)[4]) {
-        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-    }
+    static __device__ __forceinline__ float4 load4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+    static __device__ __forceinline__ void store4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 };
 template <> struct Io<__nv_bfloat16> {
-    static __device__ __forceinline__ void load4(const __nv_bfloat16* p, float (&v)[4]) {
+    static __device__ __forceinline__ float4 load4(const __nv_bfloat16* p) {
         const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
-        v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xFFFF0000u);
-        v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xFFFF0000u);
+        return make_float4(__uint_as_float(t.x << 16), __uint_as_float(t.x & 0xFFFF0000u), __uint_as_float(t.y << 16), __uint_as_float(t.y & 0xFFFF0000u));
     }
-    static __device__ __forceinline__ void store4(__nv_bfloat16* p, const float (&v)[4]) {
-        __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    static __device__ __forceinline__ void store4(__nv_bfloat16* p, float4 v) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
         uint2 t; t.x = *reinterpret_cast<uint32_t*>(&a); t.y = *reinterpret_cast<uint32_t*>(&b);
         *reinterpret_cast<uint2*>(p) = t;
     }
 };
 
-template <typename T, int DH, int NMAX>
-__global__ void __launch_bounds__(128)
-node_attention_kernel(const T* __restrict__ qkv, T* __restrict__ out, int B, int N, int H) {
+__device__ __forceinline__ void att_ffma2(float2& d, float2 a, float2 b) {
+    unsigned long long dd = *reinterpret_cast<unsigned long long*>(&d), aa = *reinterpret_cast<unsigned long long*>(&a), bb = *reinterpret_cast<unsigned long long*>(&b);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dd) : "l"(aa), "l"(bb));
+    d = *reinterpret_cast<float2*>(&dd);
+}
+__device__ __forceinline__ void att_ffma2s(float2& d, float a, float2 b) {
+    unsigned long long dd = *reinterpret_cast<unsigned long long*>(&d), bb = *reinterpret_cast<unsigned long long*>(&b), aa;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dd) : "l"(aa), "l"(bb));
+    d = *reinterpret_cast<float2*>(&dd);
+}
+
+constexpr int ATT_WARPS = 4;
+
+// NEXACT > 0: the node count is a compile-time constant (all index arithmetic of the tile copy folds away and the
+// score loops carry no guards); NEXACT == 0: any N <= NMAX at run time.
+template <typename T, int DH, int NMAX, int NEXACT>
+__global__ void __launch_bounds__(ATT_WARPS * 32)
+node_attention_kernel(const T* __restrict__ qkv, T* __restrict__ out, long long tasks, int N_rt, int H) {
+    const int N = NEXACT > 0 ? NEXACT : N_rt;
+    constexpr int LD = DH + 4;                       // padded row (floats)
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
-    if (wid >= (long long)B * H) return;
-    const int b = (int)(wid / H), h = (int)(wid % H);
-    float* Ks = smem + (size_t)warp * 2 * NMAX * DH;
-    float* Vs = Ks + NMAX * DH;
+    float* Qs = smem + (size_t)warp * 3 * NMAX * LD;
+    float* Ks = Qs + NMAX * LD;
+    float* Vs = Ks + NMAX * LD;
     const int HD = H * DH;
     const long long row_stride = 3LL * HD;
-    const T* base = qkv + (long long)b * N * row_stride + h * DH;
-    for (int i = lane; i < N * (DH / 4); i += 32) {
-        const int j = i / (DH / 4), c4 = i % (DH / 4);
-        const T* r = base + j * row_stride + 4 * c4;
-        float kv[4], vv[4];
-        Io<T>::load4(r + HD, kv);
-        Io<T>::load4(r + 2 * HD, vv);
-        *reinterpret_cast<float4*>(Ks + j * DH + 4 * c4) = make_float4(kv[0], kv[1], kv[2], kv[3]);
-        *reinterpret_cast<float4*>(Vs + j * DH + 4 * c4) = make_float4(vv[0], vv[1], vv[2], vv[3]);
-    }
-    __syncwarp();
     const float scale = rsqrtf((float)DH);
-    for (int n = lane; n < N; n += 32) {
-        float q[DH];
-        const T* qr = base + n * row_stride;
+    for (long long task = (long long)blockIdx.x * ATT_WARPS + warp; task < tasks; task += (long long)gridDim.x * ATT_WARPS) {
+        const long long b = task / H;
+        const int h = (int)(task % H);
+        const T* base = qkv + b * N * row_stride + h * DH;
+        __syncwarp();                                // previous task's readers are done with the tiles
+        // tile copy in batches of 8 loads per lane: all 8 are in flight before the first shared-memory store
+        // (a load -> store loop issues in order and pays one DRAM latency per iteration)
+        const int per_mat = N * (DH / 4), total4 = 3 * per_mat;
+        for (int i0 = lane; i0 < total4; i0 += 32 * 8) {
+            float4 v[8];
 #pragma unroll
-        for (int c = 0; c < DH; c += 4) {
-            float t[4];
-            Io<T>::load4(qr + c, t);
-            q[c] = t[0] * scale; q[c + 1] = t[1] * scale; q[c + 2] = t[2] * scale; q[c + 3] = t[3] * scale;
-        }
-        float sc[NMAX];
-        float mx = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < NMAX; ++j) {
-            if (j < N) {
-                float s = 0.0f;
-#pragma unroll
-                for (int c = 0; c < DH; c += 4) {
-                    const float4 kv = *reinterpret_cast<const float4*>(Ks + j * DH + c);
-                    s = fmaf(q[c], kv.x, s); s = fmaf(q[c + 1], kv.y, s);
-                    s = fmaf(q[c + 2], kv.z, s); s = fmaf(q[c + 3], kv.w, s);
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + 32 * u;
+                if (i < total4) {
+                    const int which = i / per_mat, rem = i - which * per_mat;
+                    const int j = rem / (DH / 4), c4 = rem % (DH / 4);
+                    v[u] = Io<T>::load4(base + j * row_stride + which * HD + 4 * c4);
                 }
-                sc[j] = s;
-                mx = fmaxf(mx, s);
             }
-        }
-        float acc[DH];
 #pragma unroll
-        for (int c = 0; c < DH; ++c) acc[c] = 0.0f;
-        float sum = 0.0f;
-#pragma unroll
-        for (int j = 0; j < NMAX; ++j) {
-            if (j < N) {
-                const float pj = expf(sc[j] - mx);
-                sum += pj;
-#pragma unroll
-                for (int c = 0; c < DH; c += 4) {
-                    const float4 vv = *reinterpret_cast<const float4*>(Vs + j * DH + c);
-                    acc[c] = fmaf(pj, vv.x, acc[c]); acc[c + 1] = fmaf(pj, vv.y, acc[c + 1]);
-                    acc[c + 2] = fmaf(pj, vv.z, acc[c + 2]); acc[c + 3] = fmaf(pj, vv.w, acc[c + 3]);
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + 32 * u;
+                if (i < total4) {
+                    const int which = i / per_mat, rem = i - which * per_mat;
+                    const int j = rem / (DH / 4), c4 = rem % (DH / 4);
+                    float4 t = v[u];
+                    if (which == 0) { t.x *= scale; t.y *= scale; t.z *= scale; t.w *= scale; }      // q * dh^-1/2 (attention.py:128)
+                    *reinterpret_cast<float4*>(Qs + which * NMAX * LD + j * LD + 4 * c4) = t;
                 }
             }
         }
-        const float inv = 1.0f / sum;
-        T* o = out + ((long long)b * N + n) * HD + h * DH;
+        __syncwarp();
+        for (int n = lane; n < N; n += 32) {
+            float2 q[DH / 2];
 #pragma unroll
-        for (int c = 0; c < DH; c += 4) {
-            const float t[4] = {acc[c] * inv, acc[c + 1] * inv, acc[c + 2] * inv, acc[c + 3] * inv};
-            Io<T>::store4(o + c, t);
+            for (int c = 0; c < DH; c += 4) {
+                const float4 t = *reinterpret_cast<const float4*>(Qs + n * LD + c);
+                q[c / 2] = make_float2(t.x, t.y); q[c / 2 + 1] = make_float2(t.z, t.w);
+            }
+            float sc[NMAX];
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < NMAX; ++j) {
+                if (j < N) {
+                    float2 s2[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+                    for (int c = 0; c < DH; c += 4) {       // four independent accumulator chains
+                        const float4 kv = *reinterpret_cast<const float4*>(Ks + j * LD + c);
+                        att_ffma2(s2[(c / 4) & 1], q[c / 2], make_float2(kv.x, kv.y));
+                        att_ffma2(s2[2 + ((c / 4) & 1)], q[c / 2 + 1], make_float2(kv.z, kv.w));
+                    }
+                    sc[j] = ((s2[0].x + s2[1].x) + (s2[2].x + s2[3].x)) + ((s2[0].y + s2[1].y) + (s2[2].y + s2[3].y));
+                    mx = fmaxf(mx, sc[j]);
+                }
+            }
+            float2 acc[DH / 2];
+#pragma unroll
+            for (int c = 0; c < DH / 2; ++c) acc[c] = make_float2(0.f, 0.f);
+            float sum = 0.0f;
+#pragma unroll
+            for (int j = 0; j < NMAX; ++j) {
+                if (j < N) {
+                    const float pj = expf(sc[j] - mx);
+                    sum += pj;
+#pragma unroll
+                    for (int c = 0; c < DH; c += 4) {
+                        const float4 vv = *reinterpret_cast<const float4*>(Vs + j * LD + c);
+                        att_ffma2s(acc[c / 2], pj, make_float2(vv.x, vv.y));
+                        att_ffma2s(acc[c / 2 + 1], pj, make_float2(vv.z, vv.w));
+                    }
+                }
+            }
+            const float inv = 1.0f / sum;
+            T* o = out + (b * N + n) * HD + h * DH;
+#pragma unroll
+            for (int c = 0; c < DH; c += 4)
+                Io<T>::store4(o + c, make_float4(acc[c / 2].x * inv, acc[c / 2].y * inv, acc[c / 2 + 1].x * inv, acc[c / 2 + 1].y * inv));
         }
     }
 }
 
-template <typename T, int DH, int NMAX>
+template <typename T, int DH, int NMAX, int NEXACT>
 static int launch_attention(const T* qkv, T* out, int B, int N, int H, cudaStream_t st) {
-    const int warps = 4;
-    const size_t smem = (size_t)warps * 2 * NMAX * DH * sizeof(float);
-    auto kern = node_attention_kernel<T, DH, NMAX>;
-    if (smem > 48 * 1024) SD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = (size_t)ATT_WARPS * 3 * NMAX * (DH + 4) * sizeof(float);
+    auto kern = node_attention_kernel<T, DH, NMAX, NEXACT>;
+    static bool configured = false;
+    if (!configured && smem > 48 * 1024) {
+        SD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
     const long long tasks = (long long)B * H;
-    kern<<<(unsigned)((tasks + warps - 1) / warps), warps * 32, smem, st>>>(qkv, out, B, N, H);
+    long long blocks = (tasks + ATT_WARPS - 1) / ATT_WARPS;
+    const long long cap = 148LL * 8;                 // persistent-style grid: a few CTAs per SM, tasks grid-strided
+    if (blocks > cap) blocks = cap;
+    kern<<<(unsigned)blocks, ATT_WARPS * 32, smem, st>>>(qkv, out, tasks, N, H);
     SD_LAUNCH_OK("node_attention_kernel");
     return SD_OK;
 }
@@ -120,10 +159,13 @@ static int launch_attention(const T* qkv, T* out, int B, int N, int H, cudaStrea
 template <typename T>
 static int node_attention_any(const T* qkv, T* out, int B, int N, int heads, int dh, cudaStream_t st) {
     if (B <= 0) return SD_OK;
-    if (dh == 32 && N <= 32) return launch_attention<T, 32, 32>(qkv, out, B, N, heads, st);
-    if (dh == 32 && N <= 64) return launch_attention<T, 32, 64>(qkv, out, B, N, heads, st);
-    if (dh == 16 && N <= 32) return launch_attention<T, 16, 32>(qkv, out, B, N, heads, st);
-    if (dh == 64 && N <= 32) return launch_attention<T, 64, 32>(qkv, out, B, N, heads, st);
+    if (dh == 32 && N == 21) return launch_attention<T, 32, 21, 21>(qkv, out, B, N, heads, st);    // AMASS
+    if (dh == 32 && N == 16) return launch_attention<T, 32, 16, 16>(qkv, out, B, N, heads, st);    // H36M, README
+    if (dh == 32 && N == 17) return launch_attention<T, 32, 17, 17>(qkv, out, B, N, heads, st);    // FreeMan
+    if (dh == 32 && N <= 32) return launch_attention<T, 32, 32, 0>(qkv, out, B, N, heads, st);
+    if (dh == 32 && N <= 64) return launch_attention<T, 32, 64, 0>(qkv, out, B, N, heads, st);
+    if (dh == 16 && N <= 32) return launch_attention<T, 16, 32, 0>(qkv, out, B, N, heads, st);
+    if (dh == 64 && N <= 32) return launch_attention<T, 64, 32, 0>(qkv, out, B, N, heads, st);
     set_error("node_attention: dim_head %d with %d nodes unsupported (dim_head 32: N<=64; 16/64: N<=32)", dh, N);
     return SD_ERR_UNSUPPORTED;
 }

@@ -33,12 +33,24 @@ int row_inv_norm_fp32(const float* x, float* inv, long long rows, int width, cud
 // thread = (sample, 4 latent channels); the three [N,N] tables of step t sit transposed in smem and
 // are read as warp-wide broadcasts; each input element is read once, each output written once.
 // =============================================================================================
+__device__ __forceinline__ void rs_ffma2(float2& d, float a, float2 b) {
+    unsigned long long dd = *reinterpret_cast<unsigned long long*>(&d), bb = *reinterpret_cast<unsigned long long*>(&b), aa;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dd) : "l"(aa), "l"(bb));
+    d = *reinterpret_cast<float2*>(&dd);
+}
+
+// thread = (sample, 2 latent channels): N float2 accumulators, FFMA2 with the table entry as the broadcast scalar
+// (SASS: FFMA2 Rd, Ra.F32, Rb.F32x2, Rd): N FFMA2 per input row.  Two channels per thread keep the kernel at ~90
+// registers (4-5 CTAs per SM); a 4-channel version needed 192 and ran at 8 warps per SM.  Input rows are fetched in
+// batches of RB float2 so that RB loads are in flight per thread before the first use.
 template <int N>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 reverse_step_kernel(const float* __restrict__ c1, const float* __restrict__ c2, const float* __restrict__ sm,
                     const float* __restrict__ x_t, const float* __restrict__ x0, const View eps,
                     float* __restrict__ x_out, float* __restrict__ mean_out, long long mean_sb, int D, int B, int clip) {
     constexpr int NP = (N + 3) & ~3;                 // padded column count for float4 broadcast reads
+    constexpr int RB = 7;                            // rows per load batch
     __shared__ __align__(16) float T[3][N][NP];      // T[i][k][n] = table_i[n][k]
     for (int i = threadIdx.x; i < 3 * N * NP; i += blockDim.x) {
         const int which = i / (N * NP), k = (i / NP) % N, n = i % NP;
@@ -46,33 +58,35 @@ reverse_step_kernel(const float* __restrict__ c1, const float* __restrict__ c2, 
         T[which][k][n] = (n < N && !(which == 2 && eps.ptr == nullptr)) ? __ldg(src + n * N + k) : 0.0f;
     }
     __syncthreads();
-    const int d4 = D >> 2;
+    const int d2 = D >> 1;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (long long)B * d4) return;
-    const int b = (int)(gid / d4), d = (int)(gid % d4) * 4;
-    float4 acc[NP];
+    if (gid >= (long long)B * d2) return;
+    const int b = (int)(gid / d2), d = (int)(gid % d2) * 2;
+    float2 acc[N];
 #pragma unroll
-    for (int n = 0; n < NP; ++n) acc[n] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int n = 0; n < N; ++n) acc[n] = make_float2(0.f, 0.f);
 
     auto accumulate = [&](const float* in, long long node_stride, int which, bool clamp) {
-#pragma unroll 3
-        for (int k = 0; k < N; ++k) {
-            float4 v = __ldg(reinterpret_cast<const float4*>(in + k * node_stride));
-            if (clamp) {
-                v.x = fminf(fmaxf(v.x, -1.f), 1.f); v.y = fminf(fmaxf(v.y, -1.f), 1.f);
-                v.z = fminf(fmaxf(v.z, -1.f), 1.f); v.w = fminf(fmaxf(v.w, -1.f), 1.f);
-            }
 #pragma unroll
-            for (int n = 0; n < NP; n += 4) {
-                const float4 m = *reinterpret_cast<const float4*>(&T[which][k][n]);
-                acc[n].x = fmaf(m.x, v.x, acc[n].x); acc[n].y = fmaf(m.x, v.y, acc[n].y);
-                acc[n].z = fmaf(m.x, v.z, acc[n].z); acc[n].w = fmaf(m.x, v.w, acc[n].w);
-                acc[n + 1].x = fmaf(m.y, v.x, acc[n + 1].x); acc[n + 1].y = fmaf(m.y, v.y, acc[n + 1].y);
-                acc[n + 1].z = fmaf(m.y, v.z, acc[n + 1].z); acc[n + 1].w = fmaf(m.y, v.w, acc[n + 1].w);
-                acc[n + 2].x = fmaf(m.z, v.x, acc[n + 2].x); acc[n + 2].y = fmaf(m.z, v.y, acc[n + 2].y);
-                acc[n + 2].z = fmaf(m.z, v.z, acc[n + 2].z); acc[n + 2].w = fmaf(m.z, v.w, acc[n + 2].w);
-                acc[n + 3].x = fmaf(m.w, v.x, acc[n + 3].x); acc[n + 3].y = fmaf(m.w, v.y, acc[n + 3].y);
-                acc[n + 3].z = fmaf(m.w, v.z, acc[n + 3].z); acc[n + 3].w = fmaf(m.w, v.w, acc[n + 3].w);
+        for (int k0 = 0; k0 < N; k0 += RB) {
+            float2 v[RB];
+#pragma unroll
+            for (int r = 0; r < RB; ++r)
+                if (k0 + r < N) v[r] = __ldg(reinterpret_cast<const float2*>(in + (k0 + r) * node_stride));
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                if (k0 + r < N) {
+                    float2 x = v[r];
+                    if (clamp) { x.x = fminf(fmaxf(x.x, -1.f), 1.f); x.y = fminf(fmaxf(x.y, -1.f), 1.f); }
+#pragma unroll
+                    for (int n = 0; n < NP; n += 4) {
+                        const float4 m = *reinterpret_cast<const float4*>(&T[which][k0 + r][n]);
+                        const float mm[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (n + e < N) rs_ffma2(acc[n + e], mm[e], x);
+                    }
+                }
             }
         }
     };
@@ -81,11 +95,11 @@ reverse_step_kernel(const float* __restrict__ c1, const float* __restrict__ c2, 
     accumulate(x_t + off, D, 1, false);
     if (mean_out) {
 #pragma unroll
-        for (int n = 0; n < N; ++n) *reinterpret_cast<float4*>(mean_out + (long long)b * mean_sb + d + (long long)n * D) = acc[n];
+        for (int n = 0; n < N; ++n) *reinterpret_cast<float2*>(mean_out + (long long)b * mean_sb + d + (long long)n * D) = acc[n];
     }
     if (eps.ptr) accumulate(row_ptr(eps, b, 0) + d, eps.sn, 2, false);
 #pragma unroll
-    for (int n = 0; n < N; ++n) *reinterpret_cast<float4*>(x_out + off + (long long)n * D) = acc[n];
+    for (int n = 0; n < N; ++n) *reinterpret_cast<float2*>(x_out + off + (long long)n * D) = acc[n];
 }
 
 // diagonal tables (U == I, the isotropic degenerate path): pure streaming kernel
@@ -159,7 +173,7 @@ reverse_step_generic_kernel(const float* __restrict__ c1, const float* __restric
 template <int N>
 static int launch_reverse_step(const float* c1, const float* c2, const float* s, const float* x_t, const float* x0,
                                const View& eps, float* x_out, float* mean_out, long long mean_sb, int D, int B, int clip, cudaStream_t st) {
-    const long long total = (long long)B * (D >> 2);
+    const long long total = (long long)B * (D >> 1);
     reverse_step_kernel<N><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(c1, c2, s, x_t, x0, eps, x_out, mean_out, mean_sb, D, B, clip);
     SD_LAUNCH_OK("reverse_step_kernel");
     return SD_OK;
