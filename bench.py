@@ -35,7 +35,8 @@ def parse():
     ap.add_argument("--dataset", default="amass")
     ap.add_argument("--windows", type=int, default=512, help="observed windows per GPU per step (configs/config_eval/config.yaml:27)")
     ap.add_argument("--samples", type=int, default=50)
-    ap.add_argument("--precision", default=os.environ.get("SKELDIFF_PRECISION", "fp32"), choices=["fp32", "bf16", "bf16x3"])
+    ap.add_argument("--precision", default=os.environ.get("SKELDIFF_PRECISION", "bf16x3"), choices=["fp32", "bf16", "bf16x3"],
+                    help="headline path: bf16x3 = fp32-grade tensor-core path (default), fp32 = FFMA2, bf16 = bf16 activations")
     ap.add_argument("--cpu-windows", type=int, default=64, help="windows of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--perturbed", action="store_true", help="dense non-identity graph-influence matrices (trained-model-like)")
@@ -147,59 +148,69 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def kernel_roofline(dev, spec, diff, precision, peaks):
-    """Dominant kernel (one 192->192 graph-linear of the Denoiser at the full batch) and the fused reverse
-    step, each timed alone with CUDA events; inputs are larger than L2 (126 MB)."""
+def _timed_kernel(dev, fn, iters=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize(dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+    ev[0].record()
+    for i in range(iters):
+        fn()
+        ev[i + 1].record()
+    torch.cuda.synchronize(dev)
+    return sum(ev[i].elapsed_time(ev[i + 1]) for i in range(iters)) / iters * 1e-3
+
+
+def kernel_rooflines(dev, spec, diff, peaks):
+    """The kernels that dominate each path, timed alone with CUDA events on torch's current stream (the stream the
+    library launches on) at the full batch B = 25 600; every operand set is larger than the 126 MB L2.
+    Algorithmic work per launch follows DESIGN.md section 4 / SURVEY section 8d."""
     from skeletondiffusion_b200 import _native as nv
+    lib = nv.load()
     B, N, C = 25600, spec.num_nodes, 192
-    layer = diff.model.layers[0][0].block2.proj
-    plan = layer.plan()
+    plan = diff.model.layers[0][0].block2.proj.plan()
     x = torch.randn(B, N, C, device=dev)
     res = torch.randn(B, N, C, device=dev)
     out = torch.empty(B, N, C, device=dev)
-
-    def timed(fn, iters=10):
-        for _ in range(3):
-            fn()
-        torch.cuda.synchronize(dev)
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
-        ev[0].record()
-        for i in range(iters):
-            fn()
-            ev[i + 1].record()
-        torch.cuda.synchronize(dev)
-        return sum(ev[i].elapsed_time(ev[i + 1]) for i in range(iters)) / iters * 1e-3
-
-    flops = 2.0 * B * N * C * C
+    ss = torch.zeros(1, 2 * C, device=dev)
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        pass
     src = "MEASURED_PEAKS.json" if peaks.get("_measured") else "fallback"
-    if precision == "fp32":
-        t_glin = timed(lambda: plan.forward(x, act=nv.ACT_TANH, residual=res, out=out, precision="fp32"))
-        tf = flops / t_glin / 1e12
-        roof = {"kernel": "glin_gemm_fp32_kernel: graph-linear 192->192 (+tanh +residual), FFMA, B=25600, N=%d" % N, "bound": "tensor",
-                "achieved": tf, "peak": peaks.get("bf16_tflops", 1590.0), "unit": "TFLOP/s", "frac": tf / peaks.get("bf16_tflops", 1590.0),
-                "traffic": None, "ms": t_glin * 1e3, "hbm_gbs": B * N * C * 4 * 3.0 / t_glin / 1e9, "peak_source": src}
-    else:
-        # tcgen05 kernel on its native bf16 tensors: K=192 -> 96 FLOP/B, below the B200 ridge => HBM-bound
-        lib = nv.load()
-        x16, r16, o16 = x.to(torch.bfloat16), res.to(torch.bfloat16), torch.empty(B, N, C, device=dev, dtype=torch.bfloat16)
-        ss = torch.zeros(2 * C, device=dev)
-        st = nv.stream_ptr(dev)
-        t_glin = timed(lambda: nv.check(lib.sd_glin_forward_bf16(plan.handle, x16.data_ptr(), None, ss.data_ptr(), nv.ACT_TANH, r16.data_ptr(),
-                                                                 o16.data_ptr(), 0, None, B, st), "sd_glin_forward_bf16"))
-        bytes_glin = B * N * C * 2 * 3.0        # algorithmic: read x, read residual, write out (bf16)
-        gbs = bytes_glin / t_glin / 1e9
-        roof = {"kernel": "glin_tc_kernel (tcgen05/TMEM/TMA): graph-linear 192->192 (+scale/shift +tanh +residual), bf16, B=25600, N=%d" % N,
-                "bound": "hbm", "achieved": gbs, "peak": peaks.get("hbm_gbs", 6650.0), "unit": "GB/s", "frac": gbs / peaks.get("hbm_gbs", 6650.0),
-                "traffic": None, "ms": t_glin * 1e3, "tflops": flops / t_glin / 1e12, "bytes_per_sample_layer": N * C * 2 * 3, "peak_source": src}
-    # fused reverse step: 3 reads + 1 write of [B, N, 96] fp32
+    hbm, tfl = peaks.get("hbm_gbs", 6650.0), peaks.get("bf16_tflops", 1590.0)
+    flops = 2.0 * B * N * C * C                      # algorithmic fp32 FLOPs of one 192->192 graph-linear launch
+    rl = {}
+    # (1) fp32-grade graph-linear on the tensor cores (bf16x3): 6 bf16 MMAs per fp32 product
+    t = _timed_kernel(dev, lambda: plan.forward(x, scale_shift=ss, act=nv.ACT_TANH, residual=res, out=out, precision="bf16x3"))
+    rl["glin_tc3"] = {"kernel": "glin_tc3_kernel (tcgen05, 3-plane split): graph-linear 192->192 +scale/shift +tanh +residual, fp32 I/O, B=25600",
+                      "bound": "tensor", "achieved": flops / t / 1e12, "peak": tfl, "unit": "TFLOP/s", "frac": flops / t / 1e12 / tfl,
+                      "issued_tflops_bf16": 6 * flops / t / 1e12, "issued_frac": 6 * flops / t / 1e12 / tfl,
+                      "traffic": traffic.get("glin_tc3_kernel"), "ms": t * 1e3, "flops_per_sample_layer": 2.0 * N * C * C, "peak_source": src}
+    # (2) exact-fp32 FFMA2 graph-linear
+    t = _timed_kernel(dev, lambda: plan.forward(x, scale_shift=ss, act=nv.ACT_TANH, residual=res, out=out, precision="fp32"))
+    rl["glin_ffma2"] = {"kernel": "glin_gemm_f2_kernel (FFMA2): same layer, exact fp32", "bound": "fp32 pipe (no tensor cores)",
+                        "achieved": flops / t / 1e12, "peak": 72.0, "unit": "TFLOP/s", "frac": flops / t / 1e12 / 72.0,
+                        "traffic": traffic.get("glin_gemm_f2_kernel"), "ms": t * 1e3,
+                        "peak_source": "scratch/ffma_peak.cu on this pool's B200: 71.6 TFLOP/s FFMA, 73.8 FFMA2"}
+    # (3) bf16 graph-linear on its native bf16 tensors: K = 192 -> 96 FLOP/B, below the ridge => HBM-bound
+    x16, r16, o16 = x.to(torch.bfloat16), res.to(torch.bfloat16), torch.empty(B, N, C, device=dev, dtype=torch.bfloat16)
+    st = nv.stream_ptr(dev)
+    t = _timed_kernel(dev, lambda: nv.check(lib.sd_glin_forward_bf16(plan.handle, x16.data_ptr(), None, ss.data_ptr(), nv.ACT_TANH, r16.data_ptr(),
+                                                                     o16.data_ptr(), 0, None, B, st), "sd_glin_forward_bf16"))
+    by = B * N * C * 2 * 3.0
+    rl["glin_tc_bf16"] = {"kernel": "glin_tc_kernel (tcgen05/TMEM/TMA): same layer, bf16 activations", "bound": "hbm", "achieved": by / t / 1e9,
+                          "peak": hbm, "unit": "GB/s", "frac": by / t / 1e9 / hbm, "traffic": traffic.get("glin_tc_kernel"), "ms": t * 1e3,
+                          "tflops": flops / t / 1e12, "bytes_per_sample_layer": N * C * 2 * 3, "peak_source": src}
+    # (4) fused reverse step: 3 reads + 1 write of [B, N, 96] fp32 (injected noise)
     x_t, x0, eps = (torch.randn(B, N, 96, device=dev) for _ in range(3))
-    t_step = timed(lambda: diff._reverse_step(x_t, x0, eps, 5))
-    bytes_step = 4.0 * B * N * 96 * 4
-    gbs = bytes_step / t_step / 1e9
-    roof_step = {"kernel": "fused reverse step (injected noise), B=25600", "bound": "hbm", "achieved": gbs, "peak": peaks.get("hbm_gbs", 6650.0),
-                 "unit": "GB/s", "frac": gbs / peaks.get("hbm_gbs", 6650.0), "traffic": None, "ms": t_step * 1e3,
-                 "bytes_per_sample_step": 4 * N * 96 * 4}
-    return roof, roof_step
+    t = _timed_kernel(dev, lambda: diff._reverse_step(x_t, x0, eps, 5))
+    by = 4.0 * B * N * 96 * 4
+    rl["reverse_step"] = {"kernel": "reverse_step_kernel<%d> (fused nonisotropic step, FFMA2), B=25600" % N, "bound": "hbm", "achieved": by / t / 1e9,
+                          "peak": hbm, "unit": "GB/s", "frac": by / t / 1e9 / hbm, "traffic": traffic.get("reverse_step_kernel"), "ms": t * 1e3,
+                          "bytes_per_sample_step": 4 * N * 96 * 4, "peak_source": src}
+    return rl
 
 
 def run_ours(args):
@@ -215,7 +226,6 @@ def run_ours(args):
         raise SystemExit("bench.py: device is not sm_100 (B200); this library has no other code path")
     spec = sdb.get_skeleton(args.dataset)
     ae_cpu, diff_cpu = oracle_state(spec, args.perturbed)
-    diff_cpu.precision = args.precision
     ae, diff = ae_cpu.to(dev).eval(), diff_cpu.to(dev).eval()
     W, S, ph = args.windows, args.samples, spec.pred_length
     B = W * S
@@ -223,7 +233,6 @@ def run_ours(args):
     obs_dev = obs_host.to(dev)
     pred_host = torch.empty(W, S, ph, spec.num_nodes, 3).pin_memory()
     model = (ae, diff)
-    peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         peaks["_measured"] = True
@@ -257,7 +266,9 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()) * 1e-3
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    diff.precision = args.precision
+    for _ in range(warm):
         step_resident()
     launches0 = lib.sd_launch_count()
     with ClockSampler(local_rank) as clk:
@@ -265,7 +276,19 @@ def run_ours(args):
     launches = (lib.sd_launch_count() - launches0)
     step_e2e()
     t_e2e = timed(step_e2e, args.steps)
-    # final metric exchange: per-window mean displacement of the predictions, gathered over NCCL (48 KB-class message)
+    # secondary precisions of the same pipeline (same inputs, same step definition), fewer steps
+    others = {}
+    for prec in ("bf16", "fp32", "bf16x3"):
+        if prec == args.precision:
+            continue
+        diff.precision = prec
+        for _ in range(2):
+            step_resident()
+        k = max(2, min(args.steps, 3))
+        t = timed(step_resident, k)
+        others[prec] = {"value": B * world * k / t, "unit": UNIT, "ms_per_step": t / k * 1e3}
+    diff.precision = args.precision
+    # final metric exchange: per-window statistic of the predictions, gathered over NCCL (KB-class message, outside the loop)
     p = step_resident()
     local_metric = {"mean_abs": p.abs().mean(dim=(1, 2, 3, 4))}
     gathered = gather_window_metrics(local_metric, W * world, rank, world) if world > 1 else local_metric
@@ -273,20 +296,28 @@ def run_ours(args):
         return
     motions = B * world * args.steps
     value, e2e = motions / t_res, motions / t_e2e
-    roof, roof_step = kernel_roofline(dev, spec, diff, args.precision, peaks)
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+    rl = kernel_rooflines(dev, spec, diff, peaks)
+    dominant = {"bf16x3": "glin_tc3", "fp32": "glin_ffma2", "bf16": "glin_tc_bf16"}[args.precision]
+    dtype = {"fp32": "f32 (FFMA2, exact)", "bf16": "bf16 (tcgen05; stated tolerance, tests/test_gpu_tc.py)",
+             "bf16x3": "f32-grade: fp32 operands split into 3 bf16 planes on tcgen05, fp32 accumulate; <=1e-4 vs the reference (tests/test_gpu_tc.py)"}[args.precision]
+    if "bf16" in others:
+        others["bf16"]["note"] = "bf16 activations between layers; latents within 5e-2, ADE/FDE/APD within 2 % of the fp32 reference (tests/test_gpu_tc.py)"
+    if "fp32" in others:
+        others["fp32"]["note"] = "exact fp32 on the FFMA2 pipe, no tensor cores"
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp32": "f32", "bf16": "bf16", "bf16x3": "bf16x3 (fp32-grade split)"}[args.precision],
+            "dtype": dtype,
             "data": "synthetic observations (N(0,0.3^2) clipped to the unit box), reference-style random-init weights" +
                     (" with dense perturbed graph-influence matrices" if args.perturbed else ""),
             "config": {"workload": f"{args.dataset} eval config: {W} windows x {S} samples = {B} motions per GPU per step; encode({spec.obs_length} frames) -> 10-step sampling -> decode({ph} frames)",
                        "windows_per_gpu": W, "samples": S, "timesteps": 10, "pred_length": ph, "num_nodes": spec.num_nodes,
                        "parallelism": f"windows sharded over {world} GPU(s), no in-loop collective", "precision": args.precision,
-                       "l2_policy": "per-step working set (activations 413 MB per tensor) exceeds the 126 MB L2; no flush needed"},
+                       "l2_policy": "per-step working set (activations 413 MB per tensor, noise 1.9 GB) exceeds the 126 MB L2; no flush needed"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": obs_host.numel() * 4 * world, "d2h_bytes_per_step": pred_host.numel() * 4 * world,
                     "ms_per_step": t_e2e / args.steps * 1e3},
-            "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof, "roofline_step": roof_step,
-            "gathered_windows": int(gathered["mean_abs"].numel())}
+            "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": rl[dominant],
+            "roofline_other_kernels": {k: v for k, v in rl.items() if k != dominant},
+            "other_precisions": others, "gathered_windows": int(gathered["mean_abs"].numel())}
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)

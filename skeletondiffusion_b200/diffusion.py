@@ -128,6 +128,8 @@ class LatentDiffusion(nn.Module):
                           ("sqrt_alphas_cumprod", torch.sqrt(ac))):
             self.register_buffer(name, val.to(torch.float32))
         self._noise_calls = 0
+        self.use_cuda_graph = bool(kwargs.get("use_cuda_graph", False))
+        self._graphs = {}
 
     def set_normalization_statistics(self, statistics_pred, statistics_obs):
         self.statistics_pred, self.statistics_obs = statistics_pred, statistics_obs
@@ -300,6 +302,49 @@ class NonisotropicGaussianDiffusion(LatentDiffusion):
                                            nv.stream_ptr(x.device)), "sd_reverse_step")
         return out, mean
 
+    # ------------------------------------------------------------------ whole loop as one CUDA graph
+    def _graph_sample(self, dplan, mplan, img, x_cond, rep, sampling_noise, mean_t, B, clip_denoised, ws, prec):
+        """Replays the T-step loop (~50 launches per step) as ONE captured CUDA graph.  Graphs are cached per
+        (batch, conditioning geometry, precision, plan identity); inputs are copied into the graph's static buffers."""
+        device = img.device
+        key = (B, None if x_cond is None else tuple(x_cond.shape), rep, prec, bool(clip_denoised), mean_t is not None,
+               dplan["handle"].value, mplan.handle.value, ws.data_ptr())
+        entry = self._graphs.get(key)
+        lib = nv.load()
+        if entry is None:
+            st = dict(x=torch.empty_like(img), cond=None if x_cond is None else torch.empty_like(x_cond),
+                      noise=None if sampling_noise is None else torch.empty_like(sampling_noise),
+                      means=None if mean_t is None else torch.empty_like(mean_t))
+
+            def run():
+                cv = nv.view_of(st["cond"], rep) if st["cond"] is not None else None
+                nv.check(lib.sd_sample_loop(dplan["handle"], mplan.handle, st["x"].data_ptr(), C.byref(cv) if cv is not None else None,
+                                            nv.dptr(st["noise"]), nv.dptr(st["means"]), B, 1 if clip_denoised else 0, ws.data_ptr(),
+                                            prec, nv.stream_ptr(device)), "sd_sample_loop")
+
+            for name, src in (("x", img), ("cond", x_cond), ("noise", sampling_noise)):
+                if st[name] is not None:
+                    st[name].copy_(src)
+            side = torch.cuda.Stream(device)
+            side.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(side):
+                run()                                   # warm-up outside capture (function attributes, tensor maps)
+            torch.cuda.current_stream(device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                run()
+            entry = self._graphs[key] = dict(graph=graph, st=st)
+        st = entry["st"]
+        st["x"].copy_(img)
+        if x_cond is not None:
+            st["cond"].copy_(x_cond)
+        if sampling_noise is not None:
+            st["noise"].copy_(sampling_noise)
+        entry["graph"].replay()
+        if mean_t is not None:
+            mean_t.copy_(st["means"])
+        return st["x"].clone()
+
     @torch.no_grad()
     def p_sample(self, x, t: int, x_self_cond=None, clip_denoised=True, sampling_noise=None, *args, x_cond=None,
                  if_interpolate=False, noise2interpolate=None, interpolation_kwargs: Dict = None, **kwargs):
@@ -372,10 +417,13 @@ class NonisotropicGaussianDiffusion(LatentDiffusion):
             lib = nv.load()
             prec = nv.PRECISIONS[self.precision]
             ws = Workspace.get(device, lib.sd_sample_workspace_bytes(dplan["handle"], mplan.handle, B, prec), "sample")
-            cv = nv.view_of(x_cond, rep) if x_cond is not None else None
-            nv.check(lib.sd_sample_loop(dplan["handle"], mplan.handle, img.data_ptr(), C.byref(cv) if cv is not None else None,
-                                        nv.dptr(sampling_noise), nv.dptr(mean_t), B, 1 if clip_denoised else 0, ws.data_ptr(),
-                                        prec, nv.stream_ptr(device)), "sd_sample_loop")
+            if self.use_cuda_graph:
+                img = self._graph_sample(dplan, mplan, img, x_cond, rep, sampling_noise, mean_t, B, clip_denoised, ws, prec)
+            else:
+                cv = nv.view_of(x_cond, rep) if x_cond is not None else None
+                nv.check(lib.sd_sample_loop(dplan["handle"], mplan.handle, img.data_ptr(), C.byref(cv) if cv is not None else None,
+                                            nv.dptr(sampling_noise), nv.dptr(mean_t), B, 1 if clip_denoised else 0, ws.data_ptr(),
+                                            prec, nv.stream_ptr(device)), "sd_sample_loop")
             noise_t, imgs = sampling_noise, None
         noise = noise0
         if return_sampling_noise:

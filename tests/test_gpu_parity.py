@@ -271,3 +271,23 @@ def test_cpu_tensor_is_rejected(cuda_device):
     layer = sdb.StaticGraphLinear(8, 8, num_nodes=4).to(cuda_device)
     with pytest.raises(nv.NativeError):
         layer(torch.zeros(2, 4, 8))
+
+
+def test_cuda_graph_sampling_matches_eager(cuda_device):
+    """The whole p_sample_loop captured as one CUDA graph (replayed twice with different inputs) equals the eager loop."""
+    case = G.load_npz("h36m_perturbed")
+    spec, ae, diff, _, _ = G.dataset_models(case, device=cuda_device)
+    d = cuda_device
+    W, S = int(case["windows"]), int(case["samples"])
+    kw = dict(batch_size=W * S, x_cond=case["z_past"].to(d), start_noise=case["start_noise"].to(d), sampling_noise=case["sampling_noise"].to(d))
+    eager, _ = diff.sample(**kw)
+    diff.use_cuda_graph = True
+    g1, _ = diff.sample(**kw)
+    kw2 = dict(kw, start_noise=kw["start_noise"].flip(0).contiguous())
+    diff.use_cuda_graph = False
+    eager2, _ = diff.sample(**kw2)
+    diff.use_cuda_graph = True
+    g2, _ = diff.sample(**kw2)
+    assert len(diff._graphs) == 1
+    assert torch.equal(g1, eager) and torch.equal(g2, eager2)
+    assert G.rel_err(g1.cpu(), case["latents"]) < FP32_TOL
