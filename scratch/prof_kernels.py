@@ -31,6 +31,14 @@ def tc3():
     plan.forward(x, scale_shift=ss, act=nv.ACT_TANH, residual=res, out=out, precision="bf16x3")
 
 
+def tc3nr():
+    plan.forward(x, scale_shift=ss, act=nv.ACT_TANH, out=out, precision="bf16x3")
+
+
+def tc3raw():
+    plan.forward(x, out=out, precision="bf16x3")
+
+
 def ffma():
     plan.forward(x, scale_shift=ss, act=nv.ACT_TANH, residual=res, out=out, precision="fp32")
 
@@ -43,7 +51,7 @@ def attn():
     nv.check(lib.sd_node_attention(qkv.data_ptr(), att.data_ptr(), B, N, 8, 32, st), "attn")
 
 
-fns = {"tc": tc, "tc3": tc3, "ffma": ffma, "step": step, "attn": attn}
+fns = {"tc": tc, "tc3": tc3, "tc3nr": tc3nr, "tc3raw": tc3raw, "ffma": ffma, "step": step, "attn": attn}
 sel = list(fns) if which == "all" else which.split(",")
 for name in sel:
     fn = fns[name]

@@ -88,9 +88,14 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
-    const long long total = (long long)p.N * p.NT * p.MT;
-    const long long item_lo = total * blockIdx.x / gridDim.x;
-    const long long item_hi = total * (blockIdx.x + 1) / gridDim.x;
+    // Gang scheduling: the NT CTAs of a gang walk the same (node, m-tile) sequence at the same time, each for its own
+    // 96-column n-tile, so the activation tile fetched by one of them is an L2 hit for the others (in group-major order
+    // the second read came from DRAM again: 2x A traffic in the first ncu capture).  Weights change only per node.
+    const int my_nt = (int)(blockIdx.x % p.NT);
+    const long long gang = blockIdx.x / p.NT, n_gangs = gridDim.x / p.NT;
+    const long long total = (long long)p.N * p.MT;
+    const long long item_lo = total * gang / n_gangs;
+    const long long item_hi = total * (gang + 1) / n_gangs;
     const int KB0 = p.a0.width / T3_BK;
 
     if (warp < 8) {
@@ -108,7 +113,7 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
             if (q >= q_end) return;
             const long long it = item_lo + q / p.KB;
             const int kb = (int)(q % p.KB);
-            const int mt = (int)(it % p.MT), node = (int)((it / p.MT) / p.NT);
+            const int mt = (int)(it % p.MT), node = (int)(it / p.MT);
             const View& seg = kb < KB0 ? p.a0 : p.a1;
             const int koff = (kb < KB0 ? kb : kb - KB0) * T3_BK + col4 * 4;
 #pragma unroll
@@ -150,7 +155,7 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
             long long cur_g = -1;
             for (long long it = item_lo; it < item_hi; ++it) {
                 const long long g = it / p.MT;
-                const int node = (int)(g / p.NT), nt = (int)(g % p.NT);
+                const int node = (int)g, nt = my_nt;
                 if (g != cur_g) {
                     // the previous group's MMAs (w_empty phase w_loads-1) must have retired before the tile is overwritten
                     if (w_loads > 0) mbar_wait(&bars->w_empty, (w_loads - 1) & 1u);
@@ -204,7 +209,7 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
         for (long long it = item_lo; it < item_hi; ++it) {
             const long long g = it / p.MT;
             const int mt = (int)(it % p.MT);
-            const int node = (int)(g / p.NT), nt = (int)(g % p.NT);
+            const int node = (int)g, nt = my_nt;
             const int o0 = nt * p.BN;
             if (g != cur_g) {
                 asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -245,10 +250,10 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
                     o[q].y = fmaf(__uint_as_float(v[4 * q + 1]) * rs, m4.y, a4.y);
                     o[q].z = fmaf(__uint_as_float(v[4 * q + 2]) * rs, m4.z, a4.z);
                     o[q].w = fmaf(__uint_as_float(v[4 * q + 3]) * rs, m4.w, a4.w);
-                    if (ACT == SD_ACT_TANH) { o[q].x = tanh_acc(o[q].x); o[q].y = tanh_acc(o[q].y); o[q].z = tanh_acc(o[q].z); o[q].w = tanh_acc(o[q].w); }
+                    if (ACT == SD_ACT_TANH) { o[q].x = tanhf(o[q].x); o[q].y = tanhf(o[q].y); o[q].z = tanhf(o[q].z); o[q].w = tanhf(o[q].w); }
                     if (ACT == SD_ACT_TANH_TANH) {
-                        o[q].x = tanh_acc(tanh_acc(o[q].x)); o[q].y = tanh_acc(tanh_acc(o[q].y));
-                        o[q].z = tanh_acc(tanh_acc(o[q].z)); o[q].w = tanh_acc(tanh_acc(o[q].w));
+                        o[q].x = tanhf(tanhf(o[q].x)); o[q].y = tanhf(tanhf(o[q].y));
+                        o[q].z = tanhf(tanhf(o[q].z)); o[q].w = tanhf(tanhf(o[q].w));
                     }
                     if (HAS_RES) { o[q].x += rr[q].x; o[q].y += rr[q].y; o[q].z += rr[q].z; o[q].w += rr[q].w; }
                 }
@@ -358,8 +363,10 @@ int glin_tc3_launch(const sd_glin* L, const GlinCall& c, const ViewW& out, bool 
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long long total = (long long)p.N * p.NT * p.MT;
-    const int grid = (int)(total < sms ? total : sms);
+    long long gangs = sms / p.NT;
+    if (gangs < 1) gangs = 1;
+    if (gangs > (long long)p.N * p.MT) gangs = (long long)p.N * p.MT;
+    const int grid = (int)(gangs * p.NT);
     if (act == SD_ACT_NONE) return has_res ? t3_launch_t<SD_ACT_NONE, true>(mw, p, grid, smem, st) : t3_launch_t<SD_ACT_NONE, false>(mw, p, grid, smem, st);
     if (act == SD_ACT_TANH) return has_res ? t3_launch_t<SD_ACT_TANH, true>(mw, p, grid, smem, st) : t3_launch_t<SD_ACT_TANH, false>(mw, p, grid, smem, st);
     if (act == SD_ACT_TANH_TANH) return has_res ? t3_launch_t<SD_ACT_TANH_TANH, true>(mw, p, grid, smem, st) : t3_launch_t<SD_ACT_TANH_TANH, false>(mw, p, grid, smem, st);
