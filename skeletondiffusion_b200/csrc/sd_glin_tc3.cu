@@ -2,14 +2,17 @@
 //
 // fp32 operands are split into three bf16 planes, x = x0 + x1 + x2 (8 mantissa bits each, exact), and
 //     x . w  ~=  x0 w0 + x0 w1 + x0 w2 + x1 w0 + x1 w1 + x2 w0        (terms below 2^-24 |x||w| dropped)
-// is accumulated in fp32 in TMEM: six tcgen05.mma.kind::f16 per K = 16 step.  Activations stay fp32 in
+// is accumulated in fp32 in TMEM: six tcgen05.mma.kind::f16 per K = 16 step.
+// The tensor core TRUNCATES when it adds a K = 16 partial sum to the accumulator (measured, scratch/acc_bias.py: with
+// all six pairs in one accumulator the result was 12.5 ulp short in magnitude at K = 192, 7x the rms error of an FFMA
+// chain).  So x0 w0 goes to a "main" accumulator (K/16 truncating adds) and the five small pairs to a second one whose
+// truncation error is 2^-8 of that; the epilogue adds the two with one round-to-nearest FADD.  Activations stay fp32 in
 // HBM (4 B/element, the whole non-GEMM pipeline of the fp32 path is reused unchanged); the split happens
 // on the way into shared memory:
-//   warps 0-3  transform producers: coalesced LDG.128 of the fp32 tile rows (any sd_view: in-place repeat,
+//   warps 0-7  transform producers: coalesced LDG.128 of the fp32 tile rows (any sd_view: in-place repeat,
 //              two K segments), split, STS.64 into three SWIZZLE_128B K-major plane tiles, fence.proxy.async
-//   warp 4     TMA loads of the pre-split weight planes (resident per (node, n-tile) group) + MMA issue
-//   warp 5     TMEM allocator
-//   warps 8-11 epilogue: tcgen05.ld, row scale, bias, scale/shift, accurate tanhf, fp32 residual, fp32 store (tanh via tanh_acc)
+//   warp 12    TMEM allocator, TMA loads of the pre-split weight planes (resident per (node, n-tile) group), MMA issue
+//   warps 8-11 epilogue: tcgen05.ld (main + corr), row scale, bias, scale/shift, libdevice tanhf, fp32 residual, fp32 store
 // MMA-bound by construction: 6 x 2*K*OUT FLOP per row at the bf16 rate = the cost of an fp32-accurate GEMM
 // on a machine whose TF32 rate is half the bf16 rate.
 //
@@ -170,12 +173,13 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
                 }
                 mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.BN;
+                // two accumulators per tile: x0 w0 alone in "main", the five 2^-8 .. 2^-16 pairs in "corr" (see header)
+                const uint32_t d_main = tmem_base + acc * 2u * (uint32_t)p.BN, d_corr = d_main + (uint32_t)p.BN;
                 for (int kb = 0; kb < p.KB; ++kb) {
                     mbar_wait(&bars->full[stage], phase);
                     tc_fence_after();
                     const uint32_t a_base = smem_u32(a_smem + (size_t)stage * T3_STAGE_BYTES);
-                    uint32_t first = (kb == 0) ? 1u : 0u;
+                    uint32_t first_main = (kb == 0) ? 1u : 0u, first_corr = first_main;
 #pragma unroll
                     for (int pa = 0; pa < 3; ++pa) {
 #pragma unroll
@@ -183,9 +187,11 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
                             if (pa + pw > 2) continue;
                             const uint64_t adesc = umma_desc_sw128(a_base + (uint32_t)pa * T3_BM * 128);
                             const uint64_t bdesc = umma_desc_sw128(smem_u32(w_smem + (size_t)(pw * p.KB + kb) * w_block));
+                            const bool main_pair = (pa + pw == 0);
 #pragma unroll
                             for (int k = 0; k < T3_BK / 16; ++k) {
-                                umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, first ? 0u : 1u);
+                                uint32_t& first = main_pair ? first_main : first_corr;
+                                umma_bf16(main_pair ? d_main : d_corr, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, first ? 0u : 1u);
                                 first = 0u;
                             }
                         }
@@ -236,11 +242,14 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
             }
             mbar_wait(&bars->acc_full[acc], acc_phase);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (uint32_t)p.BN;
+            const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 2u * (uint32_t)p.BN;
             for (int c0 = 0; c0 < p.BN; c0 += 16) {
-                uint32_t v[16];
+                uint32_t v[16], vc[16];
                 tmem_ld_32x16(t_row + (uint32_t)c0, v);
+                tmem_ld_32x16(t_row + (uint32_t)(p.BN + c0), vc);
                 tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(vc[j]));   // one RN add
                 float4 o[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -289,7 +298,7 @@ static int t3_stages(int K, int bn) {
     return (int)(n > T3_MAX_STAGES ? T3_MAX_STAGES : n);
 }
 static int t3_pick_bn(int K, int OUT) {
-    const int cands[] = {192, 128, 96, 64, 32};
+    const int cands[] = {128, 96, 64, 32};    // 4 accumulators of BN fp32 columns must fit the 512 TMEM columns
     for (int bn : cands) if (OUT % bn == 0 && t3_stages(K, bn) >= 2) return bn;
     return 0;
 }
@@ -330,7 +339,7 @@ int glin_tc3_launch(const sd_glin* L, const GlinCall& c, const ViewW& out, bool 
     p.a0 = c.a0; p.a1 = c.a1; if (!c.a1.ptr) { p.a1 = c.a0; p.a1.width = 0; }
     p.B = c.B; p.N = L->N; p.K = L->K; p.OUT = L->OUT; p.BN = t3_pick_bn(L->K, L->OUT); p.NT = L->OUT / p.BN;
     p.MT = (c.B + T3_BM - 1) / T3_BM; p.KB = L->K / T3_BK; p.nstage = t3_stages(L->K, p.BN); p.n_types = L->n_types;
-    p.tmem_cols = 2 * p.BN <= 32 ? 32 : (2 * p.BN <= 64 ? 64 : (2 * p.BN <= 128 ? 128 : (2 * p.BN <= 256 ? 256 : 512)));
+    p.tmem_cols = 4 * p.BN <= 32 ? 32 : (4 * p.BN <= 64 ? 64 : (4 * p.BN <= 128 ? 128 : (4 * p.BN <= 256 ? 256 : 512)));   // (main + corr) x 2 buffers
     p.types = L->types;
     p.out = out;
     int act = SD_ACT_NONE;
