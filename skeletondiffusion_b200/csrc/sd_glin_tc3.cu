@@ -112,21 +112,36 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
         // while the current one is split and stored (a 3-deep pipeline does not fit the 128-register budget).
         int stage = 0; uint32_t phase = 0;
         const long long q_end = (item_hi - item_lo) * p.KB;       // flattened (tile, k-block) sequence
-        auto fetch = [&](long long q, float4 (&v)[8]) {
-            if (q >= q_end) return;
-            const long long it = item_lo + q / p.KB;
-            const int kb = (int)(q % p.KB);
-            const int mt = (int)(it % p.MT), node = (int)(it / p.MT);
-            const View& seg = kb < KB0 ? p.a0 : p.a1;
-            const int koff = (kb < KB0 ? kb : kb - KB0) * T3_BK + col4 * 4;
+        // The (node, m-tile, k-block) position of the fetch stream advances incrementally and views without an in-place
+        // repeat take a division-free path: in the first ncu capture two thirds of the producers' 860 instructions per
+        // thread and k-block were 64-bit / runtime-divisor integer divisions (q / KB, it % MT, b / rep per row).
+        int f_kb = 0, f_mt = (int)(item_lo % p.MT), f_node = (int)(item_lo / p.MT);
+        long long f_left = q_end, e_left = q_end;
+        auto fetch = [&](float4 (&v)[8]) {
+            if (f_left <= 0) return;
+            --f_left;
+            const bool seg0 = f_kb < KB0;
+            const View& seg = seg0 ? p.a0 : p.a1;
+            const float* base = seg.ptr + (long long)f_node * seg.sn + ((seg0 ? f_kb : f_kb - KB0) * T3_BK + col4 * 4);
+            const int b0 = f_mt * T3_BM + row0;
+            if (seg.rep == 1) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int b = mt * T3_BM + row0 + 16 * i;
-                v[i] = (b < p.B) ? __ldg(reinterpret_cast<const float4*>(row_ptr(seg, b, node) + koff)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = 0; i < 8; ++i) {
+                    const int b = b0 + 16 * i;
+                    v[i] = (b < p.B) ? __ldg(reinterpret_cast<const float4*>(base + (long long)b * seg.sb)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int b = b0 + 16 * i;
+                    v[i] = (b < p.B) ? __ldg(reinterpret_cast<const float4*>(base + (long long)(b / seg.rep) * seg.sb)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             }
+            if (++f_kb == p.KB) { f_kb = 0; if (++f_mt == p.MT) { f_mt = 0; ++f_node; } }
         };
-        auto emit = [&](long long q, const float4 (&v)[8]) {
-            if (q >= q_end) return;
+        auto emit = [&](const float4 (&v)[8]) {
+            if (e_left <= 0) return;
+            --e_left;
             mbar_wait(&bars->empty[stage], phase ^ 1);
             uint8_t* st = a_smem + (size_t)stage * T3_STAGE_BYTES;
 #pragma unroll
@@ -145,10 +160,10 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
             if (++stage == p.nstage) { stage = 0; phase ^= 1; }
         };
         float4 va[8], vb[8];
-        fetch(0, va);
+        fetch(va);
         for (long long q = 0; q < q_end; q += 2) {
-            fetch(q + 1, vb); emit(q, va);
-            fetch(q + 2, va); emit(q + 1, vb);
+            fetch(vb); emit(va);
+            fetch(va); emit(vb);
         }
     } else if (warp == T3_MMA_WARP) {
         // ================================================================ weight TMA + MMA issue
