@@ -61,6 +61,10 @@ __device__ __forceinline__ void split3(float x, uint32_t& h, uint32_t& m, uint32
     const float r2 = r1 - __uint_as_float(m);
     l = __float_as_uint(r2) & 0xFFFF0000u;
 }
+// Bulk L2 prefetch: brings `bytes` (multiple of 16) at p into L2 without occupying registers or shared memory.
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
+}
 // (hi16 of b) << 16 | (hi16 of a): two bf16 packed in element order a, b
 __device__ __forceinline__ uint32_t pack_hi(uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x7632); }
 
@@ -74,7 +78,8 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
     uint8_t* a_smem = w_smem + (size_t)3 * p.KB * w_block;         // [stage][plane][128 x 128 B]
     float* epi_mul = reinterpret_cast<float*>(a_smem + (size_t)p.nstage * T3_STAGE_BYTES);
     float* epi_add = epi_mul + p.BN;
-    T3Barriers* bars = reinterpret_cast<T3Barriers*>(epi_add + p.BN);
+    float* epi_stage = epi_add + p.BN;                             // 4 warps x [32 rows][16 floats], swizzled
+    T3Barriers* bars = reinterpret_cast<T3Barriers*>(epi_stage + 4 * 32 * 16);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -225,6 +230,8 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
         // ================================================================ epilogue (warps 8-11: warp % 4 = lane quarter)
         const int quarter = warp & 3;
         const int et = threadIdx.x - T3_EPI_WARP0 * 32;
+        float* stg = epi_stage + quarter * (32 * 16);
+        const int tr = lane >> 2, tc4 = lane & 3;
         uint32_t acc = 0, acc_phase = 0;
         long long cur_g = -1;
         for (long long it = item_lo; it < item_hi; ++it) {
@@ -244,16 +251,34 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 cur_g = g;
             }
-            const int b = mt * T3_BM + quarter * 32 + lane;
-            const bool valid = b < p.B;
-            const float rs = (valid && p.row_scale) ? __ldg(p.row_scale + (long long)b * p.N + node) : 1.0f;
-            const float* res_row = (HAS_RES && valid) ? row_ptr(p.residual, b, node) + o0 : nullptr;
-            float* out_row = valid ? row_ptr(p.out, b, node) + o0 : nullptr;
-            // 16-column chunks; the residual of chunk c+1 is in flight while chunk c is computed and stored
+            // TMEM hands each lane one ROW of the tile; stored that way every LDG/STG.128 of a warp would touch 32
+            // different rows (32 LSU wavefronts per instruction: in the second ncu capture the residual alone cost 140 us).
+            // Each 16-column chunk is therefore transposed through a 2 KB swizzled staging tile: afterwards four lanes
+            // cover the 64 contiguous bytes of a row and one instruction touches 8 rows.
+            const int b_own = mt * T3_BM + quarter * 32 + lane;
+            const float rs = (b_own < p.B && p.row_scale) ? __ldg(p.row_scale + (long long)b_own * p.N + node) : 1.0f;
+            const int bT0 = mt * T3_BM + quarter * 32 + tr;                  // transposed mapping: rows bT0 + 8 j
+            const float* res_base = nullptr;
+            if (HAS_RES) res_base = p.residual.ptr + (long long)node * p.residual.sn + o0 + 4 * tc4;
+            float* out_base = p.out.ptr + (long long)node * p.out.sn + o0 + 4 * tc4;
+            long long res_off[4];
             float4 rr[4];
-            if (HAS_RES && valid) {
+            if (HAS_RES) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) rr[q] = __ldg(reinterpret_cast<const float4*>(res_row) + q);
+                for (int j = 0; j < 4; ++j) {
+                    const int bj = bT0 + 8 * j;
+                    res_off[j] = (long long)(p.residual.rep == 1 ? bj : bj / p.residual.rep) * p.residual.sb;
+                    if (bj < p.B) rr[j] = __ldg(reinterpret_cast<const float4*>(res_base + res_off[j]));
+                }
+            }
+            if (HAS_RES && it + 1 < item_hi) {
+                // The epilogue keeps one 2 KB residual chunk per warp in flight, far too little to cover DRAM latency;
+                // the NEXT tile's residual rows (one per thread) are pulled into L2 while this tile is processed.
+                const long long it2 = it + 1;
+                const int b2 = (int)(it2 % p.MT) * T3_BM + quarter * 32 + lane, node2 = (int)(it2 / p.MT);
+                if (b2 < p.B)
+                    prefetch_l2_bulk(p.residual.ptr + (long long)(p.residual.rep == 1 ? b2 : b2 / p.residual.rep) * p.residual.sb +
+                                     (long long)node2 * p.residual.sn + o0, (uint32_t)p.BN * 4u);
             }
             mbar_wait(&bars->acc_full[acc], acc_phase);
             tc_fence_after();
@@ -263,31 +288,41 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
                 tmem_ld_32x16(t_row + (uint32_t)c0, v);
                 tmem_ld_32x16(t_row + (uint32_t)(p.BN + c0), vc);
                 tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(vc[j]));   // one RN add
-                float4 o[4];
+                __syncwarp();                                   // the previous chunk has been read out of the staging tile
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const float4 m4 = *reinterpret_cast<const float4*>(epi_mul + c0 + 4 * q);
-                    const float4 a4 = *reinterpret_cast<const float4*>(epi_add + c0 + 4 * q);
-                    o[q].x = fmaf(__uint_as_float(v[4 * q + 0]) * rs, m4.x, a4.x);
-                    o[q].y = fmaf(__uint_as_float(v[4 * q + 1]) * rs, m4.y, a4.y);
-                    o[q].z = fmaf(__uint_as_float(v[4 * q + 2]) * rs, m4.z, a4.z);
-                    o[q].w = fmaf(__uint_as_float(v[4 * q + 3]) * rs, m4.w, a4.w);
-                    if (ACT == SD_ACT_TANH) { o[q].x = tanhf(o[q].x); o[q].y = tanhf(o[q].y); o[q].z = tanhf(o[q].z); o[q].w = tanhf(o[q].w); }
+                    float4 x;                                   // main + corr: one round-to-nearest add, then the row scale
+                    x.x = (__uint_as_float(v[4 * q + 0]) + __uint_as_float(vc[4 * q + 0])) * rs;
+                    x.y = (__uint_as_float(v[4 * q + 1]) + __uint_as_float(vc[4 * q + 1])) * rs;
+                    x.z = (__uint_as_float(v[4 * q + 2]) + __uint_as_float(vc[4 * q + 2])) * rs;
+                    x.w = (__uint_as_float(v[4 * q + 3]) + __uint_as_float(vc[4 * q + 3])) * rs;
+                    *reinterpret_cast<float4*>(stg + lane * 16 + 4 * (q ^ ((lane >> 1) & 3))) = x;
+                }
+                __syncwarp();
+                const float4 m4 = *reinterpret_cast<const float4*>(epi_mul + c0 + 4 * tc4);
+                const float4 a4 = *reinterpret_cast<const float4*>(epi_add + c0 + 4 * tc4);
+                float4 o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 x = *reinterpret_cast<const float4*>(stg + (tr + 8 * j) * 16 + 4 * (tc4 ^ ((tr >> 1) & 3)));
+                    o[j].x = fmaf(x.x, m4.x, a4.x); o[j].y = fmaf(x.y, m4.y, a4.y);
+                    o[j].z = fmaf(x.z, m4.z, a4.z); o[j].w = fmaf(x.w, m4.w, a4.w);
+                    if (ACT == SD_ACT_TANH) { o[j].x = tanhf(o[j].x); o[j].y = tanhf(o[j].y); o[j].z = tanhf(o[j].z); o[j].w = tanhf(o[j].w); }
                     if (ACT == SD_ACT_TANH_TANH) {
-                        o[q].x = tanhf(tanhf(o[q].x)); o[q].y = tanhf(tanhf(o[q].y));
-                        o[q].z = tanhf(tanhf(o[q].z)); o[q].w = tanhf(tanhf(o[q].w));
+                        o[j].x = tanhf(tanhf(o[j].x)); o[j].y = tanhf(tanhf(o[j].y));
+                        o[j].z = tanhf(tanhf(o[j].z)); o[j].w = tanhf(tanhf(o[j].w));
                     }
-                    if (HAS_RES) { o[q].x += rr[q].x; o[q].y += rr[q].y; o[q].z += rr[q].z; o[q].w += rr[q].w; }
+                    if (HAS_RES) { o[j].x += rr[j].x; o[j].y += rr[j].y; o[j].z += rr[j].z; o[j].w += rr[j].w; }
                 }
-                if (HAS_RES && valid && c0 + 16 < p.BN) {
+                if (HAS_RES && c0 + 16 < p.BN) {                // the next chunk's residual is in flight during this chunk's stores
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) rr[q] = __ldg(reinterpret_cast<const float4*>(res_row + c0 + 16) + q);
+                    for (int j = 0; j < 4; ++j)
+                        if (bT0 + 8 * j < p.B) rr[j] = __ldg(reinterpret_cast<const float4*>(res_base + res_off[j] + c0 + 16));
                 }
-                if (valid) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(out_row + c0 + 4 * q) = o[q];
+                for (int j = 0; j < 4; ++j) {
+                    const int bj = bT0 + 8 * j;
+                    if (bj < p.B) *reinterpret_cast<float4*>(out_base + (long long)bj * p.out.sb + c0) = o[j];
                 }
             }
             tc_fence_before();
@@ -305,7 +340,7 @@ typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static size_t t3_fixed_smem(int K, int bn) { return (size_t)3 * (K / T3_BK) * bn * 128 + 2 * (size_t)bn * 4 + sizeof(T3Barriers) + 1024; }
+static size_t t3_fixed_smem(int K, int bn) { return (size_t)3 * (K / T3_BK) * bn * 128 + 2 * (size_t)bn * 4 + 4 * 32 * 16 * 4 + sizeof(T3Barriers) + 1024; }
 static int t3_stages(int K, int bn) {
     const size_t budget = 227 * 1024, fixed = t3_fixed_smem(K, bn);
     if (fixed + 2 * (size_t)T3_STAGE_BYTES > budget) return 0;
