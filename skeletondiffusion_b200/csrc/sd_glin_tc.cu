@@ -73,7 +73,9 @@ glin_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                const __grid_constant__ CUtensorMap map_w, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // layout: [W: KB blocks of BN x 128 B][A: NSTAGE x 16 KB][epilogue tables 2 x BN floats][barriers]
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment (SWIZZLE_128B atoms) by pointer arithmetic on the __shared__ array: rounding the address up through
+    // uintptr_t made the compiler lose the address space and emit generic LD/ST for every shared-memory access of the kernel.
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t w_block_bytes = (uint32_t)p.BN * 128u;
     uint8_t* w_smem = smem;
     uint8_t* a_smem = w_smem + (size_t)p.KB * w_block_bytes;

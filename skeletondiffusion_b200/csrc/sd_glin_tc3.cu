@@ -72,7 +72,9 @@ template <int ACT, bool HAS_RES>
 __global__ void __launch_bounds__(T3_THREADS, 1)
 glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment (SWIZZLE_128B atoms) by pointer arithmetic on the __shared__ array: rounding the address up through
+    // uintptr_t made the compiler lose the address space and emit generic LD/ST for every shared-memory access of the kernel.
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t w_block = (uint32_t)p.BN * 128u;                 // one (plane, k-block) weight tile
     uint8_t* w_smem = smem;                                        // [plane][kb][BN x 128 B]
     uint8_t* a_smem = w_smem + (size_t)3 * p.KB * w_block;         // [stage][plane][128 x 128 B]
