@@ -7,7 +7,9 @@
 // on the packed FFMA2 pipe: q.k as float2 partial sums over channel pairs, p_j * v_j as scalar x float2.
 // qkv / out are fp32 (parity path) or bf16 (tensor-core path); the math is fp32 in both.
 #include "sd_internal.h"
+#include "sd_tc.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace sd {
 
@@ -156,9 +158,212 @@ static int launch_attention(const T* qkv, T* out, int B, int N, int H, cudaStrea
     return SD_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Bulk-copy pipeline (fp32, 8 heads x 32 channels): the shipped Denoiser configuration.
+//
+// One sample's qkv rows are ONE contiguous block in HBM (N x 768 floats = 64.5 KB for AMASS) and so is its output
+// (N x 256 floats).  A persistent CTA streams whole samples through a 3-deep shared-memory ring with one
+// cp.async.bulk per sample issued by a copy warp (no register staging, no per-warp DRAM latency), eight compute warps
+// (warp = head, lane = query node) read Q, K and V IN PLACE, and the normalised output is staged in shared memory and
+// written back with one bulk store per sample.
+// The rows of a block are 3072 B apart, i.e. every row starts at bank 0: lanes reading THEIR OWN row chunk by chunk
+// would conflict 8 ways.  Lane n therefore visits the eight 16-byte chunks of its q row (and of its output row) in
+// the rotated order (i + n) & 7, which 8 consecutive lanes serve from 8 different bank groups, and undoes the
+// rotation in registers with a 3-stage conditional rotate (SELs, no LSU traffic).  K and V rows are read in natural
+// order by all lanes at once: pure broadcasts, one LSU wavefront per LDS.128 (a first version rotated those reads as
+// well, which made every one of the 336 K/V loads per head a 4-wavefront access and the kernel LSU-bound at 1.1 ms).
+constexpr int AB_HEADS = 8, AB_DH = 32, AB_STAGES = 3;
+constexpr int AB_THREADS = (AB_HEADS + 1) * 32;      // 8 compute warps + 1 copy warp
+
+struct __align__(8) AbBarriers { uint64_t full[AB_STAGES], empty[AB_STAGES]; };
+
+__device__ __forceinline__ void ab_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(tc::smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(tc::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void ab_bulk_store(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(tc::smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ab_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void ab_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void ab_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// x[i] <- x[(i - r) & 7] (DIR = -1) or x[(i + r) & 7] (DIR = +1) for every set bit r of n: rotation of 8 float4 slots by n
+template <int DIR>
+__device__ __forceinline__ void ab_rotate8(float4 (&x)[8], int n) {
+#pragma unroll
+    for (int r = 1; r < 8; r <<= 1) {
+        const bool on = (n & r) != 0;
+        float4 t[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] = x[(i + DIR * r) & 7];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            x[i].x = on ? t[i].x : x[i].x; x[i].y = on ? t[i].y : x[i].y;
+            x[i].z = on ? t[i].z : x[i].z; x[i].w = on ? t[i].w : x[i].w;
+        }
+    }
+}
+
+template <int N>
+__global__ void __launch_bounds__(AB_THREADS, 1)
+node_attention_bulk_kernel(const float* __restrict__ qkv, float* __restrict__ out, int B) {
+    constexpr int ROW = 3 * AB_HEADS * AB_DH;                       // 768 floats per (sample, node) row: q | k | v, each [head][32]
+    constexpr int IN_FLOATS = N * ROW, OUT_ROW = AB_HEADS * AB_DH, OUT_FLOATS = N * OUT_ROW;
+    constexpr uint32_t IN_BYTES = IN_FLOATS * 4u, OUT_BYTES = OUT_FLOATS * 4u;
+    extern __shared__ __align__(128) float ab_smem[];
+    float* in_buf = ab_smem;                                        // [AB_STAGES][IN_FLOATS]
+    float* out_buf = in_buf + AB_STAGES * IN_FLOATS;                // [OUT_FLOATS]
+    AbBarriers* bars = reinterpret_cast<AbBarriers*>(out_buf + OUT_FLOATS);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < AB_STAGES; ++s) { tc::mbar_init(&bars->full[s], 1); tc::mbar_init(&bars->empty[s], AB_HEADS); }
+        tc::fence_barrier_init();
+    }
+    __syncthreads();
+    if (warp == AB_HEADS) {
+        // ------------------------------------------------------------ copy warp: one bulk copy per sample
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int b = blockIdx.x; b < B; b += gridDim.x) {
+                tc::mbar_wait(&bars->empty[stage], phase ^ 1);
+                tc::mbar_arrive_expect_tx(&bars->full[stage], IN_BYTES);
+                ab_bulk_load(in_buf + stage * IN_FLOATS, qkv + (long long)b * IN_FLOATS, IN_BYTES, &bars->full[stage]);
+                if (++stage == AB_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+        return;
+    }
+    // ---------------------------------------------------------------- compute warps: warp = head, lane = query node
+    const int h = warp, n = lane;
+    const bool active = n < N;
+    const float scale = rsqrtf((float)AB_DH);
+    int rot[8];                                                     // float offset of the chunk visited at position i
+#pragma unroll
+    for (int i = 0; i < 8; ++i) rot[i] = 4 * ((i + n) & 7);
+    int stage = 0; uint32_t phase = 0;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        tc::mbar_wait(&bars->full[stage], phase);
+        const float* blk = in_buf + stage * IN_FLOATS + h * AB_DH;
+        float2 acc[16];
+        float inv = 0.0f;
+        if (active) {
+            float2 q[16];
+            const float* qrow = blk + n * ROW;
+            {
+                float4 qs[8];                                       // slot i = chunk (i + n) & 7
+#pragma unroll
+                for (int i = 0; i < 8; ++i) qs[i] = *reinterpret_cast<const float4*>(qrow + rot[i]);
+                ab_rotate8<-1>(qs, n);                              // slot k = chunk k
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    q[2 * i] = make_float2(qs[i].x * scale, qs[i].y * scale);   // q * dh^-1/2 (attention.py:128)
+                    q[2 * i + 1] = make_float2(qs[i].z * scale, qs[i].w * scale);
+                }
+            }
+            float sc[N];
+            float mx = -INFINITY;
+            const float* kbase = blk + AB_HEADS * AB_DH;
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                float2 s2[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {                       // four independent accumulator chains
+                    const float4 kv = *reinterpret_cast<const float4*>(kbase + j * ROW + 4 * i);       // broadcast
+                    att_ffma2(s2[i & 1], q[2 * i], make_float2(kv.x, kv.y));
+                    att_ffma2(s2[2 + (i & 1)], q[2 * i + 1], make_float2(kv.z, kv.w));
+                }
+                sc[j] = ((s2[0].x + s2[1].x) + (s2[2].x + s2[3].x)) + ((s2[0].y + s2[1].y) + (s2[2].y + s2[3].y));
+                mx = fmaxf(mx, sc[j]);
+            }
+#pragma unroll
+            for (int c = 0; c < 16; ++c) acc[c] = make_float2(0.f, 0.f);
+            float sum = 0.0f;
+            const float* vbase = blk + 2 * AB_HEADS * AB_DH;
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                const float pj = expf(sc[j] - mx);
+                sum += pj;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 vv = *reinterpret_cast<const float4*>(vbase + j * ROW + 4 * i);       // broadcast
+                    att_ffma2s(acc[2 * i], pj, make_float2(vv.x, vv.y));
+                    att_ffma2s(acc[2 * i + 1], pj, make_float2(vv.z, vv.w));
+                }
+            }
+            inv = 1.0f / sum;
+        }
+        // every warp is done with the input block: hand the stage back to the copy warp
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&bars->empty[stage]);
+        // the previous sample's bulk store must have finished READING out_buf before it is overwritten
+        if (threadIdx.x == 0) ab_bulk_wait_read();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (active) {
+            float* orow = out_buf + n * OUT_ROW + h * AB_DH;
+            float4 os[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) os[i] = make_float4(acc[2 * i].x * inv, acc[2 * i].y * inv, acc[2 * i + 1].x * inv, acc[2 * i + 1].y * inv);
+            ab_rotate8<1>(os, n);                                   // slot i = chunk (i + n) & 7
+#pragma unroll
+            for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(orow + rot[i]) = os[i];
+        }
+        tc::fence_proxy_async();                                    // generic-proxy writes -> visible to the bulk store (async proxy)
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (threadIdx.x == 0) {
+            ab_bulk_store(out + (long long)b * OUT_FLOATS, out_buf, OUT_BYTES);
+            ab_bulk_commit();
+        }
+        if (++stage == AB_STAGES) { stage = 0; phase ^= 1; }
+    }
+    if (threadIdx.x == 0) ab_bulk_wait_all();                       // shared memory must outlive the last store
+}
+
+template <int N>
+static int launch_attention_bulk(const float* qkv, float* out, int B, cudaStream_t st) {
+    constexpr size_t smem = (size_t)(AB_STAGES * N * 3 + N) * AB_HEADS * AB_DH * sizeof(float) + sizeof(AbBarriers) + 128;
+    static_assert(smem <= 227 * 1024, "attention ring does not fit shared memory");
+    auto kern = node_attention_bulk_kernel<N>;
+    static bool configured = false;
+    if (!configured) {
+        SD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = B < sms ? B : sms;                             // persistent: one CTA per SM, samples grid-strided
+    kern<<<grid, AB_THREADS, smem, st>>>(qkv, out, B);
+    SD_LAUNCH_OK("node_attention_bulk_kernel");
+    return SD_OK;
+}
+
+static bool attention_legacy_forced() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SKELDIFF_ATTENTION_LEGACY"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
+template <typename T> struct BulkAttention {
+    static bool run(const T*, T*, int, int, int, int, cudaStream_t, int*) { return false; }
+};
+template <> struct BulkAttention<float> {
+    // returns true when the shape was handled (rc holds the status)
+    static bool run(const float* qkv, float* out, int B, int N, int heads, int dh, cudaStream_t st, int* rc) {
+        if (heads != AB_HEADS || dh != AB_DH || attention_legacy_forced()) return false;
+        if ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out)) & 15u) return false;
+        if (N == 21) { *rc = launch_attention_bulk<21>(qkv, out, B, st); return true; }    // AMASS
+        if (N == 16) { *rc = launch_attention_bulk<16>(qkv, out, B, st); return true; }    // H36M, README
+        if (N == 17) { *rc = launch_attention_bulk<17>(qkv, out, B, st); return true; }    // FreeMan
+        return false;
+    }
+};
+
 template <typename T>
 static int node_attention_any(const T* qkv, T* out, int B, int N, int heads, int dh, cudaStream_t st) {
     if (B <= 0) return SD_OK;
+    int rc = SD_OK;
+    if (BulkAttention<T>::run(qkv, out, B, N, heads, dh, st, &rc)) return rc;
     if (dh == 32 && N == 21) return launch_attention<T, 32, 21, 21>(qkv, out, B, N, heads, st);    // AMASS
     if (dh == 32 && N == 16) return launch_attention<T, 32, 16, 16>(qkv, out, B, N, heads, st);    // H36M, README
     if (dh == 32 && N == 17) return launch_attention<T, 32, 17, 17>(qkv, out, B, N, heads, st);    // FreeMan
