@@ -164,8 +164,8 @@ static int launch_attention(const T* qkv, T* out, int B, int N, int H, cudaStrea
 // One sample's qkv rows are ONE contiguous block in HBM (N x 768 floats = 64.5 KB for AMASS) and so is its output
 // (N x 256 floats).  A persistent CTA streams whole samples through a 3-deep shared-memory ring with one
 // cp.async.bulk per sample issued by a copy warp (no register staging, no per-warp DRAM latency), eight compute warps
-// (warp = head, lane = query node) read Q, K and V IN PLACE, and the normalised output is staged in shared memory and
-// written back with one bulk store per sample.
+// (warp = head, lane = query node) read Q, K and V IN PLACE, write the normalised output over their own q slice, and
+// the copy warp writes it back with bulk stores; the compute warps never synchronise with each other.
 // The rows of a block are 3072 B apart, i.e. every row starts at bank 0: lanes reading THEIR OWN row chunk by chunk
 // would conflict 8 ways.  Lane n therefore visits the eight 16-byte chunks of its q row (and of its output row) in
 // the rotated order (i + n) & 7, which 8 consecutive lanes serve from 8 different bank groups, and undoes the
@@ -175,7 +175,7 @@ static int launch_attention(const T* qkv, T* out, int B, int N, int H, cudaStrea
 constexpr int AB_HEADS = 8, AB_DH = 32, AB_STAGES = 3;
 constexpr int AB_THREADS = (AB_HEADS + 1) * 32;      // 8 compute warps + 1 copy warp
 
-struct __align__(8) AbBarriers { uint64_t full[AB_STAGES], empty[AB_STAGES]; };
+struct __align__(8) AbBarriers { uint64_t full[AB_STAGES], done[AB_STAGES]; };
 
 __device__ __forceinline__ void ab_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -213,24 +213,39 @@ node_attention_bulk_kernel(const float* __restrict__ qkv, float* __restrict__ ou
     constexpr uint32_t IN_BYTES = IN_FLOATS * 4u, OUT_BYTES = OUT_FLOATS * 4u;
     extern __shared__ __align__(128) float ab_smem[];
     float* in_buf = ab_smem;                                        // [AB_STAGES][IN_FLOATS]
-    float* out_buf = in_buf + AB_STAGES * IN_FLOATS;                // [OUT_FLOATS]
-    AbBarriers* bars = reinterpret_cast<AbBarriers*>(out_buf + OUT_FLOATS);
+    AbBarriers* bars = reinterpret_cast<AbBarriers*>(in_buf + AB_STAGES * IN_FLOATS);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < AB_STAGES; ++s) { tc::mbar_init(&bars->full[s], 1); tc::mbar_init(&bars->empty[s], AB_HEADS); }
+        for (int s = 0; s < AB_STAGES; ++s) { tc::mbar_init(&bars->full[s], 1); tc::mbar_init(&bars->done[s], AB_HEADS); }
         tc::fence_barrier_init();
     }
     __syncthreads();
+    const int my_samples = blockIdx.x < B ? (B - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     if (warp == AB_HEADS) {
-        // ------------------------------------------------------------ copy warp: one bulk copy per sample
+        // ------------------------------------------------------------ copy warp: bulk load per sample, bulk stores of its result
+        // Head h writes its normalised output over ITS OWN q slice of the stage (a q row and an output row are both
+        // [8 heads][32] floats), so the compute warps never synchronise with each other: each arrives on done[stage]
+        // when its slice is written, and this thread stores the N output rows (1 KB each, 3 KB apart in shared memory),
+        // waits until they have been read and re-arms the stage with the sample three positions ahead.
         if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (int b = blockIdx.x; b < B; b += gridDim.x) {
-                tc::mbar_wait(&bars->empty[stage], phase ^ 1);
-                tc::mbar_arrive_expect_tx(&bars->full[stage], IN_BYTES);
-                ab_bulk_load(in_buf + stage * IN_FLOATS, qkv + (long long)b * IN_FLOATS, IN_BYTES, &bars->full[stage]);
-                if (++stage == AB_STAGES) { stage = 0; phase ^= 1; }
+            auto load = [&](int k) {
+                const int st = k % AB_STAGES;
+                tc::mbar_arrive_expect_tx(&bars->full[st], IN_BYTES);
+                ab_bulk_load(in_buf + st * IN_FLOATS, qkv + ((long long)blockIdx.x + (long long)k * gridDim.x) * IN_FLOATS, IN_BYTES, &bars->full[st]);
+            };
+            for (int k = 0; k < AB_STAGES && k < my_samples; ++k) load(k);
+            for (int k = 0; k < my_samples; ++k) {
+                const int st = k % AB_STAGES;
+                tc::mbar_wait(&bars->done[st], (uint32_t)(k / AB_STAGES) & 1u);
+                float* dst = out + ((long long)blockIdx.x + (long long)k * gridDim.x) * OUT_FLOATS;
+                const float* src = in_buf + st * IN_FLOATS;
+#pragma unroll 1
+                for (int r = 0; r < N; ++r) ab_bulk_store(dst + r * OUT_ROW, src + r * ROW, OUT_ROW * 4u);
+                ab_bulk_commit();
+                ab_bulk_wait_read();                                // the stage may be overwritten
+                if (k + AB_STAGES < my_samples) load(k + AB_STAGES);
             }
+            ab_bulk_wait_all();                                     // shared memory must outlive the last store
         }
         return;
     }
@@ -241,15 +256,13 @@ node_attention_bulk_kernel(const float* __restrict__ qkv, float* __restrict__ ou
     int rot[8];                                                     // float offset of the chunk visited at position i
 #pragma unroll
     for (int i = 0; i < 8; ++i) rot[i] = 4 * ((i + n) & 7);
-    int stage = 0; uint32_t phase = 0;
-    for (int b = blockIdx.x; b < B; b += gridDim.x) {
-        tc::mbar_wait(&bars->full[stage], phase);
-        const float* blk = in_buf + stage * IN_FLOATS + h * AB_DH;
-        float2 acc[16];
-        float inv = 0.0f;
+    for (int k = 0; k < my_samples; ++k) {
+        const int stage = k % AB_STAGES;
+        tc::mbar_wait(&bars->full[stage], (uint32_t)(k / AB_STAGES) & 1u);
+        float* blk = in_buf + stage * IN_FLOATS + h * AB_DH;
         if (active) {
             float2 q[16];
-            const float* qrow = blk + n * ROW;
+            float* qrow = blk + n * ROW;
             {
                 float4 qs[8];                                       // slot i = chunk (i + n) & 7
 #pragma unroll
@@ -276,6 +289,7 @@ node_attention_bulk_kernel(const float* __restrict__ qkv, float* __restrict__ ou
                 sc[j] = ((s2[0].x + s2[1].x) + (s2[2].x + s2[3].x)) + ((s2[0].y + s2[1].y) + (s2[2].y + s2[3].y));
                 mx = fmaxf(mx, sc[j]);
             }
+            float2 acc[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) acc[c] = make_float2(0.f, 0.f);
             float sum = 0.0f;
@@ -291,37 +305,23 @@ node_attention_bulk_kernel(const float* __restrict__ qkv, float* __restrict__ ou
                     att_ffma2s(acc[2 * i + 1], pj, make_float2(vv.z, vv.w));
                 }
             }
-            inv = 1.0f / sum;
-        }
-        // every warp is done with the input block: hand the stage back to the copy warp
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&bars->empty[stage]);
-        // the previous sample's bulk store must have finished READING out_buf before it is overwritten
-        if (threadIdx.x == 0) ab_bulk_wait_read();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (active) {
-            float* orow = out_buf + n * OUT_ROW + h * AB_DH;
+            const float inv = 1.0f / sum;
             float4 os[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) os[i] = make_float4(acc[2 * i].x * inv, acc[2 * i].y * inv, acc[2 * i + 1].x * inv, acc[2 * i + 1].y * inv);
             ab_rotate8<1>(os, n);                                   // slot i = chunk (i + n) & 7
 #pragma unroll
-            for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(orow + rot[i]) = os[i];
+            for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(qrow + rot[i]) = os[i];     // in place over this head's q slice
         }
-        tc::fence_proxy_async();                                    // generic-proxy writes -> visible to the bulk store (async proxy)
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (threadIdx.x == 0) {
-            ab_bulk_store(out + (long long)b * OUT_FLOATS, out_buf, OUT_BYTES);
-            ab_bulk_commit();
-        }
-        if (++stage == AB_STAGES) { stage = 0; phase ^= 1; }
+        tc::fence_proxy_async();                                    // generic-proxy writes -> visible to the bulk stores (async proxy)
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&bars->done[stage]);
     }
-    if (threadIdx.x == 0) ab_bulk_wait_all();                       // shared memory must outlive the last store
 }
 
 template <int N>
 static int launch_attention_bulk(const float* qkv, float* out, int B, cudaStream_t st) {
-    constexpr size_t smem = (size_t)(AB_STAGES * N * 3 + N) * AB_HEADS * AB_DH * sizeof(float) + sizeof(AbBarriers) + 128;
+    constexpr size_t smem = (size_t)(AB_STAGES * N * 3) * AB_HEADS * AB_DH * sizeof(float) + sizeof(AbBarriers) + 128;
     static_assert(smem <= 227 * 1024, "attention ring does not fit shared memory");
     auto kern = node_attention_bulk_kernel<N>;
     static bool configured = false;
