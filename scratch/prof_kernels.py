@@ -39,6 +39,22 @@ def tc3raw():
     plan.forward(x, out=out, precision="bf16x3")
 
 
+_qkv = {}
+
+
+def qkv():
+    """to_qkv shape: 192 -> 768, row scale only"""
+    if not _qkv:
+        att = diff.model.layers[0][1]
+        mod = att.fn.fn if hasattr(att, "fn") and hasattr(att.fn, "fn") else att
+        while not hasattr(mod, "to_qkv"):
+            mod = mod.fn
+        _qkv["plan"] = mod.to_qkv.plan()
+        _qkv["out"] = torch.empty(B, N, 768, device=dev)
+        _qkv["rs"] = torch.rand(B, N, device=dev) + 0.5
+    _qkv["plan"].forward(x, row_scale=_qkv["rs"], out=_qkv["out"], precision="bf16x3")
+
+
 def ffma():
     plan.forward(x, scale_shift=ss, act=nv.ACT_TANH, residual=res, out=out, precision="fp32")
 
@@ -51,7 +67,7 @@ def attn():
     nv.check(lib.sd_node_attention(qkv.data_ptr(), att.data_ptr(), B, N, 8, 32, st), "attn")
 
 
-fns = {"tc": tc, "tc3": tc3, "tc3nr": tc3nr, "tc3raw": tc3raw, "ffma": ffma, "step": step, "attn": attn}
+fns = {"qkv": qkv, "tc": tc, "tc3": tc3, "tc3nr": tc3nr, "tc3raw": tc3raw, "ffma": ffma, "step": step, "attn": attn}
 sel = list(fns) if which == "all" else which.split(",")
 for name in sel:
     fn = fns[name]

@@ -20,6 +20,7 @@
 #include "sd_internal.h"
 #include "sd_tc.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace sd {
 
@@ -28,14 +29,16 @@ using namespace sd::tc;
 constexpr int T3_BM = 128, T3_BK = 64;
 constexpr int T3_PRODUCERS = 256;   // warps 0-7 (two per scheduler hide each other's LDG latency)
 constexpr int T3_EPI_WARP0 = 8;     // warps 8-11: epilogue (warp % 4 = TMEM lane quarter)
-constexpr int T3_MMA_WARP = 12, T3_ALLOC_WARP = 12;   // warp 12: TMEM allocation, weight TMA, MMA issue
-constexpr int T3_THREADS = 416;     // 13 warps (register file is allocated as for 16: 128 registers per thread)
+constexpr int T3_MMA_WARP = 12, T3_ALLOC_WARP = 12;   // warp 12: TMEM allocation, MMA issue (+ weight TMA in the weight-resident mode)
+constexpr int T3_WLOAD_WARP = 13;   // warp 13: weight-slot TMA ring of the activation-stationary mode
+constexpr int T3_THREADS = 448;     // 14 warps (register file is allocated as for 16: 128 registers per thread)
 constexpr int T3_MAX_STAGES = 4;
 constexpr int T3_STAGE_BYTES = 3 * T3_BM * 128;    // three plane tiles of 128 rows x 128 B
 
 struct T3Params {
     View a0, a1;
     int B, N, K, OUT, BN, NT, MT, KB, nstage, n_types, tmem_cols;
+    int a_stationary;           // 1: stage ring = the K/64 k-blocks of ONE m-tile, n-tiles looped inside the CTA, weights streamed
     NodeTypes types;
     const float* row_scale;
     const float* bias_node;
@@ -47,6 +50,7 @@ struct T3Params {
 struct __align__(8) T3Barriers {
     uint64_t full[T3_MAX_STAGES], empty[T3_MAX_STAGES];
     uint64_t w_full, w_empty;
+    uint64_t ws_full[2], ws_empty[2];       // weight slots (activation-stationary mode)
     uint64_t acc_full[2], acc_empty[2];
     uint32_t tmem_base, pad;
 };
@@ -76,8 +80,8 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
     // uintptr_t made the compiler lose the address space and emit generic LD/ST for every shared-memory access of the kernel.
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t w_block = (uint32_t)p.BN * 128u;                 // one (plane, k-block) weight tile
-    uint8_t* w_smem = smem;                                        // [plane][kb][BN x 128 B]
-    uint8_t* a_smem = w_smem + (size_t)3 * p.KB * w_block;         // [stage][plane][128 x 128 B]
+    uint8_t* w_smem = smem;                                        // resident: [plane][kb][BN x 128 B]; streamed: [slot][plane][BN x 128 B]
+    uint8_t* a_smem = w_smem + (size_t)3 * (p.a_stationary ? 2 : p.KB) * w_block;   // [stage][plane][128 x 128 B]
     float* epi_mul = reinterpret_cast<float*>(a_smem + (size_t)p.nstage * T3_STAGE_BYTES);
     float* epi_add = epi_mul + p.BN;
     float* epi_stage = epi_add + p.BN;                             // 4 warps x [32 rows][16 floats], swizzled
@@ -89,6 +93,7 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
         for (int s = 0; s < p.nstage; ++s) { mbar_init(&bars->full[s], T3_PRODUCERS); mbar_init(&bars->empty[s], 1); }
         mbar_init(&bars->w_full, 1);
         mbar_init(&bars->w_empty, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&bars->ws_full[s], 1); mbar_init(&bars->ws_empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&bars->acc_full[s], 1); mbar_init(&bars->acc_empty[s], 128); }
         fence_barrier_init();
     }
@@ -101,8 +106,14 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
     // Gang scheduling: the NT CTAs of a gang walk the same (node, m-tile) sequence at the same time, each for its own
     // 96-column n-tile, so the activation tile fetched by one of them is an L2 hit for the others (in group-major order
     // the second read came from DRAM again: 2x A traffic in the first ncu capture).  Weights change only per node.
-    const int my_nt = (int)(blockIdx.x % p.NT);
-    const long long gang = blockIdx.x / p.NT, n_gangs = gridDim.x / p.NT;
+    //
+    // Activation-stationary mode (K <= 192, wide outputs): the stage ring holds the whole K of ONE m-tile, every CTA owns
+    // whole m-tiles and loops over the NT n-tiles itself while warp 13 streams the (n-tile, k-block) weight planes from
+    // L2 through a two-slot TMA ring.  The activations are fetched and split once instead of NT times (to_qkv: NT = 8).
+    const bool as_mode = p.a_stationary != 0;
+    const int my_nt = as_mode ? 0 : (int)(blockIdx.x % p.NT);
+    const int nt_lo = my_nt, nt_hi = as_mode ? p.NT : my_nt + 1;
+    const long long gang = as_mode ? blockIdx.x : blockIdx.x / p.NT, n_gangs = as_mode ? gridDim.x : gridDim.x / p.NT;
     const long long total = (long long)p.N * p.MT;
     const long long item_lo = total * gang / n_gangs;
     const long long item_hi = total * (gang + 1) / n_gangs;
@@ -173,58 +184,90 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
             fetch(va); emit(vb);
         }
     } else if (warp == T3_MMA_WARP) {
-        // ================================================================ weight TMA + MMA issue
+        // ================================================================ MMA issue (+ resident-weight TMA)
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_bf16(T3_BM, (uint32_t)p.BN);
-            int stage = 0; uint32_t phase = 0, acc = 0, acc_phase = 0, w_loads = 0;
+            int stage = 0; uint32_t phase = 0, acc = 0, acc_phase = 0, w_loads = 0, ws_cnt = 0;
             long long cur_g = -1;
             for (long long it = item_lo; it < item_hi; ++it) {
                 const long long g = it / p.MT;
-                const int node = (int)g, nt = my_nt;
-                if (g != cur_g) {
+                const int node = (int)g;
+                if (!as_mode && g != cur_g) {
                     // the previous group's MMAs (w_empty phase w_loads-1) must have retired before the tile is overwritten
                     if (w_loads > 0) mbar_wait(&bars->w_empty, (w_loads - 1) & 1u);
                     mbar_arrive_expect_tx(&bars->w_full, 3u * (uint32_t)p.KB * w_block);
                     for (int pl = 0; pl < 3; ++pl)
                         for (int kb = 0; kb < p.KB; ++kb)
-                            tma_load_3d(w_smem + (size_t)(pl * p.KB + kb) * w_block, &map_w, &bars->w_full, kb * T3_BK, nt * p.BN,
+                            tma_load_3d(w_smem + (size_t)(pl * p.KB + kb) * w_block, &map_w, &bars->w_full, kb * T3_BK, my_nt * p.BN,
                                         pl * p.n_types + p.types.t[node]);
                     mbar_wait(&bars->w_full, w_loads & 1u);
                     ++w_loads;
                     cur_g = g;
                 }
-                mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1);
-                tc_fence_after();
-                // two accumulators per tile: x0 w0 alone in "main", the five 2^-8 .. 2^-16 pairs in "corr" (see header)
-                const uint32_t d_main = tmem_base + acc * 2u * (uint32_t)p.BN, d_corr = d_main + (uint32_t)p.BN;
-                for (int kb = 0; kb < p.KB; ++kb) {
-                    mbar_wait(&bars->full[stage], phase);
+                const int stage0 = stage; const uint32_t phase0 = phase;
+                for (int nt = nt_lo; nt < nt_hi; ++nt) {
+                    stage = stage0; phase = phase0;             // as_mode: every n-tile re-reads the same KB stages
+                    mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1);
                     tc_fence_after();
-                    const uint32_t a_base = smem_u32(a_smem + (size_t)stage * T3_STAGE_BYTES);
-                    uint32_t first_main = (kb == 0) ? 1u : 0u, first_corr = first_main;
+                    // two accumulators per tile: x0 w0 alone in "main", the five 2^-8 .. 2^-16 pairs in "corr" (see header)
+                    const uint32_t d_main = tmem_base + acc * 2u * (uint32_t)p.BN, d_corr = d_main + (uint32_t)p.BN;
+                    for (int kb = 0; kb < p.KB; ++kb) {
+                        const uint8_t* w_tile = w_smem;         // plane pw of this k-block at w_tile + pw * w_plane_stride
+                        uint32_t w_plane_stride = (uint32_t)p.KB * w_block;
+                        if (as_mode) {
+                            const uint32_t slot = ws_cnt & 1u;
+                            mbar_wait(&bars->ws_full[slot], (ws_cnt >> 1) & 1u);
+                            w_tile = w_smem + (size_t)slot * 3 * w_block; w_plane_stride = w_block;
+                        } else {
+                            w_tile = w_smem + (size_t)kb * w_block;
+                        }
+                        if (nt == nt_lo) mbar_wait(&bars->full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a_base = smem_u32(a_smem + (size_t)stage * T3_STAGE_BYTES);
+                        uint32_t first_main = (kb == 0) ? 1u : 0u, first_corr = first_main;
 #pragma unroll
-                    for (int pa = 0; pa < 3; ++pa) {
+                        for (int pa = 0; pa < 3; ++pa) {
 #pragma unroll
-                        for (int pw = 0; pw < 3; ++pw) {
-                            if (pa + pw > 2) continue;
-                            const uint64_t adesc = umma_desc_sw128(a_base + (uint32_t)pa * T3_BM * 128);
-                            const uint64_t bdesc = umma_desc_sw128(smem_u32(w_smem + (size_t)(pw * p.KB + kb) * w_block));
-                            const bool main_pair = (pa + pw == 0);
+                            for (int pw = 0; pw < 3; ++pw) {
+                                if (pa + pw > 2) continue;
+                                const uint64_t adesc = umma_desc_sw128(a_base + (uint32_t)pa * T3_BM * 128);
+                                const uint64_t bdesc = umma_desc_sw128(smem_u32(w_tile + (size_t)pw * w_plane_stride));
+                                const bool main_pair = (pa + pw == 0);
 #pragma unroll
-                            for (int k = 0; k < T3_BK / 16; ++k) {
-                                uint32_t& first = main_pair ? first_main : first_corr;
-                                umma_bf16(main_pair ? d_main : d_corr, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, first ? 0u : 1u);
-                                first = 0u;
+                                for (int k = 0; k < T3_BK / 16; ++k) {
+                                    uint32_t& first = main_pair ? first_main : first_corr;
+                                    umma_bf16(main_pair ? d_main : d_corr, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, first ? 0u : 1u);
+                                    first = 0u;
+                                }
                             }
                         }
+                        if (as_mode) { umma_commit(&bars->ws_empty[ws_cnt & 1u]); ++ws_cnt; }
+                        if (nt == nt_hi - 1) umma_commit(&bars->empty[stage]);     // the planes of this k-block are no longer needed
+                        if (++stage == p.nstage) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit(&bars->empty[stage]);
-                    if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+                    umma_commit(&bars->acc_full[acc]);
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
-                umma_commit(&bars->acc_full[acc]);
                 const bool last_of_group = (it + 1 == item_hi) || ((it + 1) / p.MT != g);
-                if (last_of_group) umma_commit(&bars->w_empty);
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (!as_mode && last_of_group) umma_commit(&bars->w_empty);
+            }
+        }
+        __syncwarp();
+    } else if (warp == T3_WLOAD_WARP) {
+        // ================================================================ weight-slot TMA ring (activation-stationary mode)
+        if (as_mode && lane == 0) {
+            uint32_t cnt = 0;
+            for (long long it = item_lo; it < item_hi; ++it) {
+                const int type = p.types.t[(int)(it / p.MT)];
+                for (int nt = 0; nt < p.NT; ++nt)
+                    for (int kb = 0; kb < p.KB; ++kb, ++cnt) {
+                        const uint32_t slot = cnt & 1u;
+                        mbar_wait(&bars->ws_empty[slot], ((cnt >> 1) & 1u) ^ 1u);
+                        mbar_arrive_expect_tx(&bars->ws_full[slot], 3u * w_block);
+                        for (int pl = 0; pl < 3; ++pl)
+                            tma_load_3d(w_smem + (size_t)(slot * 3 + pl) * w_block, &map_w, &bars->ws_full[slot], kb * T3_BK, nt * p.BN,
+                                        pl * p.n_types + type);
+                    }
             }
         }
         __syncwarp();
@@ -236,10 +279,11 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
         const int tr = lane >> 2, tc4 = lane & 3;
         uint32_t acc = 0, acc_phase = 0;
         long long cur_g = -1;
-        for (long long it = item_lo; it < item_hi; ++it) {
-            const long long g = it / p.MT;
+        for (long long it = item_lo; it < item_hi; ++it)
+        for (int nt = nt_lo; nt < nt_hi; ++nt) {
+            const long long g = (it / p.MT) * p.NT + nt;          // (node, n-tile): the epilogue tables change with it
             const int mt = (int)(it % p.MT);
-            const int node = (int)g, nt = my_nt;
+            const int node = (int)(it / p.MT);
             const int o0 = nt * p.BN;
             if (g != cur_g) {
                 asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -273,14 +317,15 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
                     if (bj < p.B) rr[j] = __ldg(reinterpret_cast<const float4*>(res_base + res_off[j]));
                 }
             }
-            if (HAS_RES && it + 1 < item_hi) {
+            if (HAS_RES && (nt + 1 < nt_hi || it + 1 < item_hi)) {
                 // The epilogue keeps one 2 KB residual chunk per warp in flight, far too little to cover DRAM latency;
-                // the NEXT tile's residual rows (one per thread) are pulled into L2 while this tile is processed.
-                const long long it2 = it + 1;
+                // the NEXT pass's residual rows (one per thread) are pulled into L2 while this one is processed.
+                const long long it2 = nt + 1 < nt_hi ? it : it + 1;
+                const int o2 = (nt + 1 < nt_hi ? nt + 1 : nt_lo) * p.BN;
                 const int b2 = (int)(it2 % p.MT) * T3_BM + quarter * 32 + lane, node2 = (int)(it2 / p.MT);
                 if (b2 < p.B)
                     prefetch_l2_bulk(p.residual.ptr + (long long)(p.residual.rep == 1 ? b2 : b2 / p.residual.rep) * p.residual.sb +
-                                     (long long)node2 * p.residual.sn + o0, (uint32_t)p.BN * 4u);
+                                     (long long)node2 * p.residual.sn + o2, (uint32_t)p.BN * 4u);
             }
             mbar_wait(&bars->acc_full[acc], acc_phase);
             tc_fence_after();
@@ -342,7 +387,15 @@ typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static size_t t3_fixed_smem(int K, int bn) { return (size_t)3 * (K / T3_BK) * bn * 128 + 2 * (size_t)bn * 4 + 4 * 32 * 16 * 4 + sizeof(T3Barriers) + 1024; }
+static size_t t3_misc_smem(int bn) { return 2 * (size_t)bn * 4 + 4 * 32 * 16 * 4 + sizeof(T3Barriers) + 1024; }
+static size_t t3_fixed_smem(int K, int bn) { return (size_t)3 * (K / T3_BK) * bn * 128 + t3_misc_smem(bn); }
+// activation-stationary mode: K/64 plane stages + two weight slots of 3 planes; widest n-tile that fits (>= 64 columns)
+static int t3_as_bn(int K, int OUT) {
+    const int cands[] = {128, 96, 64};
+    for (int bn : cands)
+        if (OUT % bn == 0 && OUT / bn >= 2 && (size_t)(K / T3_BK) * T3_STAGE_BYTES + (size_t)2 * 3 * bn * 128 + t3_misc_smem(bn) <= 227 * 1024) return bn;
+    return 0;
+}
 static int t3_stages(int K, int bn) {
     const size_t budget = 227 * 1024, fixed = t3_fixed_smem(K, bn);
     if (fixed + 2 * (size_t)T3_STAGE_BYTES > budget) return 0;
@@ -391,6 +444,13 @@ int glin_tc3_launch(const sd_glin* L, const GlinCall& c, const ViewW& out, bool 
     p.a0 = c.a0; p.a1 = c.a1; if (!c.a1.ptr) { p.a1 = c.a0; p.a1.width = 0; }
     p.B = c.B; p.N = L->N; p.K = L->K; p.OUT = L->OUT; p.BN = t3_pick_bn(L->K, L->OUT); p.NT = L->OUT / p.BN;
     p.MT = (c.B + T3_BM - 1) / T3_BM; p.KB = L->K / T3_BK; p.nstage = t3_stages(L->K, p.BN); p.n_types = L->n_types;
+    p.a_stationary = 0;
+    {
+        static int as_env = -1;              // SKELDIFF_TC3_AS=0 disables the activation-stationary schedule (A/B timing)
+        if (as_env < 0) { const char* e = getenv("SKELDIFF_TC3_AS"); as_env = (e && e[0] == '0') ? 0 : 1; }
+        const int as_bn = as_env ? t3_as_bn(L->K, L->OUT) : 0;
+        if (as_bn && p.NT >= 2 && p.KB <= T3_MAX_STAGES) { p.a_stationary = 1; p.BN = as_bn; p.NT = L->OUT / as_bn; p.nstage = p.KB; }
+    }
     p.tmem_cols = 4 * p.BN <= 32 ? 32 : (4 * p.BN <= 64 ? 64 : (4 * p.BN <= 128 ? 128 : (4 * p.BN <= 256 ? 256 : 512)));   // (main + corr) x 2 buffers
     p.types = L->types;
     p.out = out;
@@ -420,14 +480,14 @@ int glin_tc3_launch(const sd_glin* L, const GlinCall& c, const ViewW& out, bool 
     CUresult r = enc(&mw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<uint16_t*>(L->W_bf16), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (weights x3) failed: %d", (int)r); return SD_ERR_CUDA; }
-    const size_t smem = t3_fixed_smem(L->K, p.BN) + (size_t)p.nstage * T3_STAGE_BYTES;
+    const size_t smem = (p.a_stationary ? (size_t)2 * 3 * p.BN * 128 + t3_misc_smem(p.BN) : t3_fixed_smem(L->K, p.BN)) + (size_t)p.nstage * T3_STAGE_BYTES;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    long long gangs = sms / p.NT;
+    long long gangs = p.a_stationary ? sms : sms / p.NT;
     if (gangs < 1) gangs = 1;
     if (gangs > (long long)p.N * p.MT) gangs = (long long)p.N * p.MT;
-    const int grid = (int)(gangs * p.NT);
+    const int grid = (int)(p.a_stationary ? gangs : gangs * p.NT);
     if (act == SD_ACT_NONE) return has_res ? t3_launch_t<SD_ACT_NONE, true>(mw, p, grid, smem, st) : t3_launch_t<SD_ACT_NONE, false>(mw, p, grid, smem, st);
     if (act == SD_ACT_TANH) return has_res ? t3_launch_t<SD_ACT_TANH, true>(mw, p, grid, smem, st) : t3_launch_t<SD_ACT_TANH, false>(mw, p, grid, smem, st);
     if (act == SD_ACT_TANH_TANH) return has_res ? t3_launch_t<SD_ACT_TANH_TANH, true>(mw, p, grid, smem, st) : t3_launch_t<SD_ACT_TANH_TANH, false>(mw, p, grid, smem, st);
