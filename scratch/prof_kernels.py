@@ -19,7 +19,7 @@ ss = torch.zeros(1, 2 * C, device=dev)
 st = nv.stream_ptr(dev)
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 x_t, x0, eps = (torch.randn(B, N, 96, device=dev) for _ in range(3))
-qkv = torch.randn(B, N, 768, device=dev)
+qkv_t = torch.randn(B, N, 768, device=dev)
 att = torch.empty(B, N, 256, device=dev)
 
 
@@ -64,7 +64,7 @@ def step():
 
 
 def attn():
-    nv.check(lib.sd_node_attention(qkv.data_ptr(), att.data_ptr(), B, N, 8, 32, st), "attn")
+    nv.check(lib.sd_node_attention(qkv_t.data_ptr(), att.data_ptr(), B, N, 8, 32, st), "attn")
 
 
 fns = {"qkv": qkv, "tc": tc, "tc3": tc3, "tc3nr": tc3nr, "tc3raw": tc3raw, "ffma": ffma, "step": step, "attn": attn}
