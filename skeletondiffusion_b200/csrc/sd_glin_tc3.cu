@@ -38,6 +38,8 @@ constexpr int T3_STAGE_BYTES = 3 * T3_BM * 128;    // three plane tiles of 128 r
 struct T3Params {
     View a0, a1;
     int B, N, K, OUT, BN, NT, MT, KB, nstage, n_types, tmem_cols;
+    int k_base;                 // first weight column of this launch (K-split of a two-segment layer)
+    View pre;                   // fp32 partial product added before the epilogue (ptr null if none)
     int a_stationary;           // 1: stage ring = the K/64 k-blocks of ONE m-tile, n-tiles looped inside the CTA, weights streamed
     NodeTypes types;
     const float* row_scale;
@@ -198,7 +200,7 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
                     mbar_arrive_expect_tx(&bars->w_full, 3u * (uint32_t)p.KB * w_block);
                     for (int pl = 0; pl < 3; ++pl)
                         for (int kb = 0; kb < p.KB; ++kb)
-                            tma_load_3d(w_smem + (size_t)(pl * p.KB + kb) * w_block, &map_w, &bars->w_full, kb * T3_BK, my_nt * p.BN,
+                            tma_load_3d(w_smem + (size_t)(pl * p.KB + kb) * w_block, &map_w, &bars->w_full, p.k_base + kb * T3_BK, my_nt * p.BN,
                                         pl * p.n_types + p.types.t[node]);
                     mbar_wait(&bars->w_full, w_loads & 1u);
                     ++w_loads;
@@ -265,7 +267,7 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
                         mbar_wait(&bars->ws_empty[slot], ((cnt >> 1) & 1u) ^ 1u);
                         mbar_arrive_expect_tx(&bars->ws_full[slot], 3u * w_block);
                         for (int pl = 0; pl < 3; ++pl)
-                            tma_load_3d(w_smem + (size_t)(slot * 3 + pl) * w_block, &map_w, &bars->ws_full[slot], kb * T3_BK, nt * p.BN,
+                            tma_load_3d(w_smem + (size_t)(slot * 3 + pl) * w_block, &map_w, &bars->ws_full[slot], p.k_base + kb * T3_BK, nt * p.BN,
                                         pl * p.n_types + type);
                     }
             }
@@ -330,7 +332,14 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
             mbar_wait(&bars->acc_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 2u * (uint32_t)p.BN;
+            const float* pre_base = p.pre.ptr ? p.pre.ptr + (long long)node * p.pre.sn + o0 + 4 * tc4 : nullptr;
             for (int c0 = 0; c0 < p.BN; c0 += 16) {
+                float4 pp[4];                                   // partial product of the first K segment (K-split layers)
+                if (pre_base) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        pp[j] = (bT0 + 8 * j < p.B) ? __ldg(reinterpret_cast<const float4*>(pre_base + (long long)(bT0 + 8 * j) * p.pre.sb + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
                 uint32_t v[16], vc[16];
                 tmem_ld_32x16(t_row + (uint32_t)c0, v);
                 tmem_ld_32x16(t_row + (uint32_t)(p.BN + c0), vc);
@@ -351,7 +360,8 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
                 float4 o[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float4 x = *reinterpret_cast<const float4*>(stg + (tr + 8 * j) * 16 + 4 * (tc4 ^ ((tr >> 1) & 3)));
+                    float4 x = *reinterpret_cast<const float4*>(stg + (tr + 8 * j) * 16 + 4 * (tc4 ^ ((tr >> 1) & 3)));
+                    if (pre_base) { x.x += pp[j].x; x.y += pp[j].y; x.z += pp[j].z; x.w += pp[j].w; }
                     o[j].x = fmaf(x.x, m4.x, a4.x); o[j].y = fmaf(x.y, m4.y, a4.y);
                     o[j].z = fmaf(x.z, m4.z, a4.z); o[j].w = fmaf(x.w, m4.w, a4.w);
                     if (ACT == SD_ACT_TANH) { o[j].x = tanhf(o[j].x); o[j].y = tanhf(o[j].y); o[j].z = tanhf(o[j].z); o[j].w = tanhf(o[j].w); }
@@ -427,10 +437,12 @@ static int t3_launch_t(const CUtensorMap& mw, const T3Params& p, int grid, size_
 }
 
 // out = epilogue(A @ W^T) with fp32 views; the caller guarantees G == identity for this call
-int glin_tc3_launch(const sd_glin* L, const GlinCall& c, const ViewW& out, bool apply_epilogue, cudaStream_t st) {
+// one launch over the weight columns [k_base, k_base + K0 + K1) of the layer; `pre` (optional) is added before the epilogue
+static int t3_launch_one(const sd_glin* L, const GlinCall& c, const ViewW& out, bool apply_epilogue, int k_base, const View* pre, cudaStream_t st) {
     if (!L->W_bf16 || L->planes != 3) { set_error("bf16x3 path: 3-plane weights not set on this layer"); return SD_ERR_INVALID; }
     const int K0 = c.a0.width, K1 = c.a1.ptr ? c.a1.width : 0;
-    if (K0 + K1 != L->K || !glin_tc3_supported(K0, K1, L->OUT)) { set_error("bf16x3 path: unsupported shape K=%d+%d OUT=%d", K0, K1, L->OUT); return SD_ERR_UNSUPPORTED; }
+    const int Kuse = K0 + K1;
+    if (k_base < 0 || k_base % T3_BK || k_base + Kuse > L->K || !glin_tc3_supported(K0, K1, L->OUT)) { set_error("bf16x3 path: unsupported shape K=%d+%d (base %d of %d) OUT=%d", K0, K1, k_base, L->K, L->OUT); return SD_ERR_UNSUPPORTED; }
     if (c.epi.ss_row_idx && apply_epilogue) { set_error("bf16x3 path: per-sample time rows are only supported on the FFMA path"); return SD_ERR_UNSUPPORTED; }
     if (c.B <= 0) return SD_OK;
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
@@ -442,13 +454,15 @@ int glin_tc3_launch(const sd_glin* L, const GlinCall& c, const ViewW& out, bool 
     }
     T3Params p;
     p.a0 = c.a0; p.a1 = c.a1; if (!c.a1.ptr) { p.a1 = c.a0; p.a1.width = 0; }
-    p.B = c.B; p.N = L->N; p.K = L->K; p.OUT = L->OUT; p.BN = t3_pick_bn(L->K, L->OUT); p.NT = L->OUT / p.BN;
-    p.MT = (c.B + T3_BM - 1) / T3_BM; p.KB = L->K / T3_BK; p.nstage = t3_stages(L->K, p.BN); p.n_types = L->n_types;
+    p.B = c.B; p.N = L->N; p.K = Kuse; p.OUT = L->OUT; p.BN = t3_pick_bn(Kuse, L->OUT); p.NT = L->OUT / p.BN;
+    p.MT = (c.B + T3_BM - 1) / T3_BM; p.KB = Kuse / T3_BK; p.nstage = t3_stages(Kuse, p.BN); p.n_types = L->n_types;
+    p.k_base = k_base;
+    if (pre) p.pre = *pre; else { p.pre.ptr = nullptr; p.pre.sb = p.pre.sn = 0; p.pre.rep = 1; p.pre.width = 0; }
     p.a_stationary = 0;
     {
         static int as_env = -1;              // SKELDIFF_TC3_AS=0 disables the activation-stationary schedule (A/B timing)
         if (as_env < 0) { const char* e = getenv("SKELDIFF_TC3_AS"); as_env = (e && e[0] == '0') ? 0 : 1; }
-        const int as_bn = as_env ? t3_as_bn(L->K, L->OUT) : 0;
+        const int as_bn = as_env ? t3_as_bn(Kuse, L->OUT) : 0;
         if (as_bn && p.NT >= 2 && p.KB <= T3_MAX_STAGES) { p.a_stationary = 1; p.BN = as_bn; p.NT = L->OUT / as_bn; p.nstage = p.KB; }
     }
     p.tmem_cols = 4 * p.BN <= 32 ? 32 : (4 * p.BN <= 64 ? 64 : (4 * p.BN <= 128 ? 128 : (4 * p.BN <= 256 ? 256 : 512)));   // (main + corr) x 2 buffers
@@ -480,7 +494,7 @@ int glin_tc3_launch(const sd_glin* L, const GlinCall& c, const ViewW& out, bool 
     CUresult r = enc(&mw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<uint16_t*>(L->W_bf16), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (weights x3) failed: %d", (int)r); return SD_ERR_CUDA; }
-    const size_t smem = (p.a_stationary ? (size_t)2 * 3 * p.BN * 128 + t3_misc_smem(p.BN) : t3_fixed_smem(L->K, p.BN)) + (size_t)p.nstage * T3_STAGE_BYTES;
+    const size_t smem = (p.a_stationary ? (size_t)2 * 3 * p.BN * 128 + t3_misc_smem(p.BN) : t3_fixed_smem(Kuse, p.BN)) + (size_t)p.nstage * T3_STAGE_BYTES;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -493,6 +507,27 @@ int glin_tc3_launch(const sd_glin* L, const GlinCall& c, const ViewW& out, bool 
     if (act == SD_ACT_TANH_TANH) return has_res ? t3_launch_t<SD_ACT_TANH_TANH, true>(mw, p, grid, smem, st) : t3_launch_t<SD_ACT_TANH_TANH, false>(mw, p, grid, smem, st);
     set_error("bf16x3 path: unknown activation %d", act);
     return SD_ERR_INVALID;
+}
+
+// out = epilogue(A @ W^T) with fp32 views; the caller guarantees G == identity for this call when apply_epilogue is set.
+// A two-segment layer whose full K cannot run activation-stationary (K = 384: 288 KB of plane stages) but whose segments can
+// is split along K: launch 1 writes the raw product of segment 0 to the caller's scratch, launch 2 adds it in front of its
+// epilogue.  Two stationary launches (0.28 + 0.33 ms) replace one weight-resident launch that re-transformed A six times (1.55 ms).
+int glin_tc3_launch(const sd_glin* L, const GlinCall& c, const ViewW& out, bool apply_epilogue, cudaStream_t st) {
+    const int K0 = c.a0.width, K1 = c.a1.ptr ? c.a1.width : 0;
+    if (K0 + K1 != L->K) { set_error("bf16x3 path: operand widths %d+%d do not match the layer's K=%d", K0, K1, L->K); return SD_ERR_INVALID; }
+    static int split_env = -1;               // SKELDIFF_TC3_KSPLIT=0 disables the K-split (A/B timing)
+    if (split_env < 0) { const char* e = getenv("SKELDIFF_TC3_KSPLIT"); split_env = (e && e[0] == '0') ? 0 : 1; }
+    auto stationary_ok = [&](int K) { return K % T3_BK == 0 && K / T3_BK <= T3_MAX_STAGES && t3_as_bn(K, L->OUT) != 0; };
+    const bool split = split_env && K1 > 0 && apply_epilogue && c.scratch && c.scratch != out.ptr && !c.row_scale && !c.epi.residual.ptr &&
+                       !stationary_ok(L->K) && stationary_ok(K0) && stationary_ok(K1);
+    if (!split) return t3_launch_one(L, c, out, apply_epilogue, 0, nullptr, st);
+    GlinCall c1 = c; c1.a1.ptr = nullptr; c1.a1.width = 0;
+    int rc = t3_launch_one(L, c1, contiguous_view_w(c.scratch, L->N, L->OUT), false, 0, nullptr, st);
+    if (rc) return rc;
+    GlinCall c2 = c; c2.a0 = c.a1; c2.a1.ptr = nullptr; c2.a1.width = 0;
+    const View pre = contiguous_view(c.scratch, L->N, L->OUT);
+    return t3_launch_one(L, c2, out, true, K0, &pre, st);
 }
 
 }  // namespace sd
