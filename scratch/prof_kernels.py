@@ -55,6 +55,21 @@ def qkv():
     _qkv["plan"].forward(x, row_scale=_qkv["rs"], out=_qkv["out"], precision="bf16x3")
 
 
+_to = {}
+
+
+def toout():
+    """to_out shape: 256 -> 192 + residual"""
+    if not _to:
+        att = diff.model.layers[0][1]
+        mod = att
+        while not hasattr(mod, "to_out"):
+            mod = mod.fn
+        _to["plan"] = mod.to_out.plan()
+        _to["x"] = torch.randn(B, N, 256, device=dev)
+    _to["plan"].forward(_to["x"], residual=res, out=out, precision="bf16x3")
+
+
 def ffma():
     plan.forward(x, scale_shift=ss, act=nv.ACT_TANH, residual=res, out=out, precision="fp32")
 
@@ -67,7 +82,7 @@ def attn():
     nv.check(lib.sd_node_attention(qkv_t.data_ptr(), att.data_ptr(), B, N, 8, 32, st), "attn")
 
 
-fns = {"qkv": qkv, "tc": tc, "tc3": tc3, "tc3nr": tc3nr, "tc3raw": tc3raw, "ffma": ffma, "step": step, "attn": attn}
+fns = {"toout": toout, "qkv": qkv, "tc": tc, "tc3": tc3, "tc3nr": tc3nr, "tc3raw": tc3raw, "ffma": ffma, "step": step, "attn": attn}
 sel = list(fns) if which == "all" else which.split(",")
 for name in sel:
     fn = fns[name]
