@@ -129,7 +129,8 @@ class GlinPlan:
         scratch = None
         if precision == "bf16":       # bf16 operand copy + fp32 raw product (see glin_forward_tc)
             scratch = Workspace.get(x.device, batch * self.N * (2 * self.in_features + 4 * self.out_features) + 1024, "glin")
-        elif not self.identity:
+        elif not self.identity or (precision == "bf16x3" and x2 is not None):
+            # pre-mix product (non-identity G^) or the partial product of a K-split two-segment layer (bf16x3)
             scratch = Workspace.get(x.device, batch * self.N * self.out_features * 4, "glin")
         args.scratch_dev = nv.dptr(scratch)
         args.batch = batch

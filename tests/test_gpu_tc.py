@@ -149,6 +149,33 @@ def test_bf16x3_graph_linear_is_fp32_grade(cuda_device, kin, kout, batch, ident)
     assert err < 3e-6, (err, err_ref)          # as close to the float64 truth as fp32 PyTorch itself (~1e-6)
 
 
+@pytest.mark.parametrize("batch", [257, 64])
+def test_bf16x3_two_segment_layer_k_split(cuda_device, batch):
+    """cat[x, skip] (192 + 192) -> 192 with identity influence: the layer runs as two activation-stationary launches, the second
+    adding the first one's partial product in front of bias / scale-shift / tanh (the final ResNet block of the Denoiser).
+    Ragged batch (257 = two full m-tiles + one row) and a batch smaller than one m-tile."""
+    import skeletondiffusion_b200 as sdb
+    from skeletondiffusion_b200 import _native as nv
+    from skeletondiffusion_b200.testing import synth_state_dict
+    spec = sdb.get_skeleton("amass")
+    N, nt = spec.num_nodes, spec.nodes_type_id
+    layer = sdb.StaticGraphLinear(384, 192, bias=True, num_nodes=N, node_types=nt, learn_influence=True)
+    sd = synth_state_dict(layer.state_dict(), seed=43, mode="perturbed", gain=1.0)
+    sd["G"] = torch.eye(N)
+    layer.load_state_dict(sd)
+    g = torch.Generator().manual_seed(batch)
+    a, b = torch.randn(batch, N, 192, generator=g), torch.randn(batch, N, 192, generator=g)
+    ss = torch.randn(1, 384, generator=g) * 0.3
+    pre64 = oc.graph_linear({k: v.double() for k, v in sd.items()}, "", torch.cat([a, b], -1).double(), nt, True)
+    ref64 = torch.tanh(pre64 * (ss[:, :192].double() + 1.0) + ss[:, 192:].double())
+    d = cuda_device
+    plan = layer.to(d).plan()
+    out = plan.forward(a.to(d), x2=b.to(d), scale_shift=ss.to(d), act=nv.ACT_TANH, precision="bf16x3")
+    exact = plan.forward(a.to(d), x2=b.to(d), scale_shift=ss.to(d), act=nv.ACT_TANH, precision="fp32")
+    assert G.rel_err(out.cpu().double(), ref64) < 3e-6
+    assert G.rel_err(out.cpu(), exact.cpu()) < 3e-6
+
+
 @pytest.mark.parametrize("name", ["amass_perturbed", "h36m_perturbed", "amass_init"])
 def test_bf16x3_pipeline_meets_fp32_gate(cuda_device, name):
     """The tensor-core fp32-grade path must pass the same <=1e-4 gate as the FFMA path, against the reference's goldens."""
