@@ -50,7 +50,7 @@ gru_step_fused_kernel(const G2Params p) {
     {   // stage h_{i-1}: chunk f = tid + 256 i -> (row = f % 128, c4 = f / 128), c4 in [0, 8 KT)
         const int row = tid & 127;
         const bool ok = b0 + row < p.B;
-        const float* src = ok ? row_ptr(p.h_prev, b0 + row, node) : nullptr;
+        const float* src = ok ? p.h_prev.ptr + (long long)(b0 + row) * p.h_prev.sb + (long long)node * p.h_prev.sn : nullptr;
 #pragma unroll
         for (int i = 0; i < 4 * KT; ++i) {
             const int c = (tid >> 7) + 2 * i, kt = c >> 3, c4 = c & 7;
@@ -142,7 +142,7 @@ gru_step_fused_kernel(const G2Params p) {
             for (int i = 0; i < 4; ++i) {
                 const int b = b0 + ty * 8 + half * 4 + i;
                 const bool ok = b < p.B;
-                const float* xrow = ok ? row_ptr(p.xr, b, node) + o0 + 2 * tx : nullptr;
+                const float* xrow = ok ? p.xr.ptr + (long long)b * p.xr.sb + (long long)node * p.xr.sn + o0 + 2 * tx : nullptr;   // rep == 1 (host check): no division
 #pragma unroll
                 for (int g = 0; g < 3; ++g) xg[i][g] = ok ? __ldg(reinterpret_cast<const float2*>(xrow + 32 * g)) : make_float2(0.f, 0.f);
             }
@@ -159,7 +159,7 @@ gru_step_fused_kernel(const G2Params p) {
                             acc[ri][1].x + bhg[1].x, acc[ri][2].x + bhg[2].x, hp.x);
                 hy.y = cell(xg[i][0].y + bxg[0].y, xg[i][1].y + bxg[1].y, xg[i][2].y + bxg[2].y, acc[ri][0].y + bhg[0].y,
                             acc[ri][1].y + bhg[1].y, acc[ri][2].y + bhg[2].y, hp.y);
-                *reinterpret_cast<float2*>(row_ptr(p.h_out, b, node) + u0) = hy;
+                *reinterpret_cast<float2*>(p.h_out.ptr + (long long)b * p.h_out.sb + (long long)node * p.h_out.sn + u0) = hy;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) yacc[ri][c] = fmaf(wfc[c][0], hy.x, fmaf(wfc[c][1], hy.y, yacc[ri][c]));
             }
@@ -180,7 +180,7 @@ gru_step_fused_kernel(const G2Params p) {
                 if (b >= p.B) continue;
                 float v = tx == 0 ? yacc[i][0] : (tx == 1 ? yacc[i][1] : yacc[i][2]);
                 if (p.bias_fc) v += __ldg(p.bias_fc + (long long)node * p.F + tx);
-                row_ptr(p.y, b, node)[tx] = tanhf(v);
+                (p.y.ptr + (long long)b * p.y.sb + (long long)node * p.y.sn)[tx] = tanhf(v);
             }
         }
     }
@@ -190,7 +190,7 @@ int gru_step_fused(const float* W_hh_perm_t, int H, const NodeTypes& types, int 
                    const View& h_prev, const ViewW& h_out, const float* Wfc, const float* bias_fc, const ViewW* y, int F, int B, cudaStream_t st) {
     if (B <= 0) return SD_OK;
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
-    if (H != 96 || !al16(W_hh_perm_t) || !al16(h_prev.ptr) || h_prev.sb % 4 || h_prev.sn % 4 || h_prev.rep != 1 || (Wfc && (F > 3 || !y))) {
+    if (H != 96 || !al16(W_hh_perm_t) || !al16(h_prev.ptr) || h_prev.sb % 4 || h_prev.sn % 4 || h_prev.rep != 1 || xr.rep != 1 || h_out.rep != 1 || (y && y->rep != 1) || (Wfc && (F > 3 || !y))) {
         set_error("gru_step_fused: unsupported configuration (H=%d F=%d)", H, F);
         return SD_ERR_UNSUPPORTED;
     }
