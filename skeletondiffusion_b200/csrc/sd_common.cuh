@@ -34,11 +34,14 @@ __host__ __device__ inline View contiguous_view(const float* p, int num_nodes, i
 __host__ __device__ inline ViewW contiguous_view_w(float* p, int num_nodes, int width) {
     ViewW r; r.ptr = p; r.sb = (long long)num_nodes * width; r.sn = width; r.rep = 1; r.width = width; return r;
 }
+// rep is a kernel parameter (uniform): views without an in-place repeat skip the ~20-instruction integer division
 __device__ __forceinline__ const float* row_ptr(const View& v, int b, int n) {
-    return v.ptr + (long long)(b / v.rep) * v.sb + (long long)n * v.sn;
+    const int s = v.rep == 1 ? b : b / v.rep;
+    return v.ptr + (long long)s * v.sb + (long long)n * v.sn;
 }
 __device__ __forceinline__ float* row_ptr(const ViewW& v, int b, int n) {
-    return v.ptr + (long long)(b / v.rep) * v.sb + (long long)n * v.sn;
+    const int s = v.rep == 1 ? b : b / v.rep;
+    return v.ptr + (long long)s * v.sb + (long long)n * v.sn;
 }
 
 // fused epilogue description shared by the GEMM and the node-mix kernels
