@@ -1,7 +1,10 @@
 // Node attention: softmax_j(q_n . k_j * dh^-1/2) v_j over the nodes of one sample, one head.
 // Reference: Attention.forward, src/core/network/layers/attention.py:125-135.
 //
-// One warp per (sample, head) task, several tasks per warp (grid-stride), lane = query node.  The head's Q/K/V rows
+// Two kernels.  node_attention_bulk_kernel<N> (below, second half of the file) is the shipped fp32 configuration (8 heads x 32
+// channels, N = 16 / 17 / 21): persistent CTAs, one cp.async.bulk per sample, Q/K/V read in place.  node_attention_kernel
+// handles every other shape and the bf16 I/O of the bf16 mode:
+// one warp per (sample, head) task, several tasks per warp (grid-stride), lane = query node.  The head's Q/K/V rows
 // ([N, dh] each) are copied into shared memory with coalesced 16-byte loads (rows padded to dh + 4 floats so that a
 // lane reading ITS OWN q row is bank-conflict free; K/V rows are read as warp-wide broadcasts).  All products run
 // on the packed FFMA2 pipe: q.k as float2 partial sums over channel pairs, p_j * v_j as scalar x float2.
