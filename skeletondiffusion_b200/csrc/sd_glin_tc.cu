@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 glin_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_w, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // layout: [W: KB blocks of BN x 128 B][A: NSTAGE x 16 KB][epilogue tables 2 x BN floats][barriers]
+    // layout: [W: KB blocks of BN x 128 B][A: NSTAGE x 16 KB][epilogue tables 2 x BN floats][epilogue staging 8 x 4 KB][barriers]
     // 1024-byte alignment (SWIZZLE_128B atoms) by pointer arithmetic on the __shared__ array: rounding the address up through
     // uintptr_t made the compiler lose the address space and emit generic LD/ST for every shared-memory access of the kernel.
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -81,7 +81,8 @@ glin_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     uint8_t* a_smem = w_smem + (size_t)p.KB * w_block_bytes;
     float* epi_mul = reinterpret_cast<float*>(a_smem + (size_t)p.nstage * TC_BM * 128);   // 16-byte aligned
     float* epi_add = epi_mul + p.BN;
-    TcBarriers* bars = reinterpret_cast<TcBarriers*>(epi_add + p.BN);
+    float* epi_stage = epi_add + p.BN;                             // TC_EPI_WARPS x [32 rows][32 floats], swizzled
+    TcBarriers* bars = reinterpret_cast<TcBarriers*>(epi_stage + TC_EPI_WARPS * 32 * 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -170,6 +171,8 @@ glin_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         const int eg = (warp - 4) >> 2;
         const int et = threadIdx.x - 128;
         constexpr int EPI_THREADS = TC_EPI_WARPS * 32;
+        float* stg = epi_stage + (warp - 4) * (32 * 32);
+        const int tr = lane >> 2, tc8 = lane & 3;
         uint32_t acc = 0, acc_phase = 0;
         long long cur_g = -1;
         for (long long it = item_lo; it < item_hi; ++it) {
@@ -189,17 +192,19 @@ glin_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
                 cur_g = g;
             }
-            const int b = mt * TC_BM + quarter * 32 + lane;
-            const bool valid = b < p.B;
-            const float rs = (valid && p.row_scale) ? __ldg(p.row_scale + (long long)b * p.N + node) : 1.0f;
-            const long long res_off = (long long)b * p.res_sb + (long long)node * p.res_sn + o0;
-            const long long out_off = (long long)b * p.out_sb + (long long)node * p.out_sn + o0;
-            // residual of this thread's first chunk is requested before waiting for the accumulator
+            // TMEM hands each lane one ROW of the tile; stored that way every LDG/STG.128 of a warp touches 32 different rows
+            // (32 LSU wavefronts per instruction).  Each 32-column chunk is transposed through a swizzled 4 KB fp32 staging tile:
+            // afterwards four lanes cover 8 columns each of one row (64 contiguous bytes of bf16) and an instruction touches 8 rows.
+            const int b_own = mt * TC_BM + quarter * 32 + lane;
+            const float rs = (b_own < p.B && p.row_scale) ? __ldg(p.row_scale + (long long)b_own * p.N + node) : 1.0f;
+            const int bT0 = mt * TC_BM + quarter * 32 + tr;                      // transposed mapping: rows bT0 + 8 j, columns 8 tc8 .. +7
+            const long long res_base = (long long)node * p.res_sn + o0 + 8 * tc8;
+            const long long out_base = (long long)node * p.out_sn + o0 + 8 * tc8;
             uint4 rr[4];
-            if (HAS_RES && valid && eg * 32 < p.BN) {
-                const uint4* rp = reinterpret_cast<const uint4*>(p.res + res_off + eg * 32);
+            if (HAS_RES && eg * 32 < p.BN) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) rr[q] = __ldg(rp + q);
+                for (int j = 0; j < 4; ++j)
+                    if (bT0 + 8 * j < p.B) rr[j] = __ldg(reinterpret_cast<const uint4*>(p.res + (long long)(bT0 + 8 * j) * p.res_sb + res_base + eg * 32));
             }
             mbar_wait(&bars->acc_full[acc], acc_phase);
             tc_fence_after();
@@ -208,44 +213,48 @@ glin_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 uint32_t v[32];
                 tmem_ld_32x32(t_row + (uint32_t)c0, v);
                 tmem_ld_wait();
-                float f[32];
+                __syncwarp();                                   // the previous chunk has been read out of the staging tile
 #pragma unroll
-                for (int j4 = 0; j4 < 32; j4 += 4) {
-                    const float4 m4 = *reinterpret_cast<const float4*>(epi_mul + c0 + j4);
-                    const float4 a4 = *reinterpret_cast<const float4*>(epi_add + c0 + j4);
-                    f[j4 + 0] = epi_act<ACT>(fmaf(__uint_as_float(v[j4 + 0]) * rs, m4.x, a4.x));
-                    f[j4 + 1] = epi_act<ACT>(fmaf(__uint_as_float(v[j4 + 1]) * rs, m4.y, a4.y));
-                    f[j4 + 2] = epi_act<ACT>(fmaf(__uint_as_float(v[j4 + 2]) * rs, m4.z, a4.z));
-                    f[j4 + 3] = epi_act<ACT>(fmaf(__uint_as_float(v[j4 + 3]) * rs, m4.w, a4.w));
-                }
-                if (HAS_RES) {
+                for (int q = 0; q < 8; ++q)
+                    *reinterpret_cast<float4*>(stg + lane * 32 + 4 * (q ^ (lane & 7))) =
+                        make_float4(__uint_as_float(v[4 * q]) * rs, __uint_as_float(v[4 * q + 1]) * rs, __uint_as_float(v[4 * q + 2]) * rs, __uint_as_float(v[4 * q + 3]) * rs);
+                __syncwarp();
+                const float4 m0 = *reinterpret_cast<const float4*>(epi_mul + c0 + 8 * tc8), m1 = *reinterpret_cast<const float4*>(epi_mul + c0 + 8 * tc8 + 4);
+                const float4 a0 = *reinterpret_cast<const float4*>(epi_add + c0 + 8 * tc8), a1 = *reinterpret_cast<const float4*>(epi_add + c0 + 8 * tc8 + 4);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const uint32_t w4[4] = {rr[q].x, rr[q].y, rr[q].z, rr[q].w};
+                for (int j = 0; j < 4; ++j) {
+                    const int row = tr + 8 * j;
+                    const float4 x0 = *reinterpret_cast<const float4*>(stg + row * 32 + 4 * ((2 * tc8) ^ (tr & 7)));
+                    const float4 x1 = *reinterpret_cast<const float4*>(stg + row * 32 + 4 * ((2 * tc8 + 1) ^ (tr & 7)));
+                    float f[8];
+                    f[0] = epi_act<ACT>(fmaf(x0.x, m0.x, a0.x)); f[1] = epi_act<ACT>(fmaf(x0.y, m0.y, a0.y));
+                    f[2] = epi_act<ACT>(fmaf(x0.z, m0.z, a0.z)); f[3] = epi_act<ACT>(fmaf(x0.w, m0.w, a0.w));
+                    f[4] = epi_act<ACT>(fmaf(x1.x, m1.x, a1.x)); f[5] = epi_act<ACT>(fmaf(x1.y, m1.y, a1.y));
+                    f[6] = epi_act<ACT>(fmaf(x1.z, m1.z, a1.z)); f[7] = epi_act<ACT>(fmaf(x1.w, m1.w, a1.w));
+                    if (HAS_RES) {
+                        const uint32_t w4[4] = {rr[j].x, rr[j].y, rr[j].z, rr[j].w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            f[q * 8 + 2 * e] += __uint_as_float(w4[e] << 16);
-                            f[q * 8 + 2 * e + 1] += __uint_as_float(w4[e] & 0xFFFF0000u);
+                            f[2 * e] += __uint_as_float(w4[e] << 16);
+                            f[2 * e + 1] += __uint_as_float(w4[e] & 0xFFFF0000u);
                         }
                     }
-                    if (valid && c0 + 64 < p.BN) {       // next chunk's residual goes in flight behind this chunk's stores
-                        const uint4* rp = reinterpret_cast<const uint4*>(p.res + res_off + c0 + 64);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) rr[q] = __ldg(rp + q);
+                    const int bj = bT0 + 8 * j;
+                    if (bj < p.B) {
+                        if (OUT_FP32) {
+                            float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + (long long)bj * p.out_sb + out_base + c0);
+                            op[0] = make_float4(f[0], f[1], f[2], f[3]);
+                            op[1] = make_float4(f[4], f[5], f[6], f[7]);
+                        } else {
+                            *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + (long long)bj * p.out_sb + out_base + c0) =
+                                make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                        }
                     }
                 }
-                if (valid) {
-                    if (OUT_FP32) {
-                        float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + out_off + c0);
+                if (HAS_RES && c0 + 64 < p.BN) {                // next chunk's residual goes in flight behind this chunk's stores
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) op[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-                    } else {
-                        uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + out_off + c0);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            op[q] = make_uint4(pack_bf16(f[8 * q], f[8 * q + 1]), pack_bf16(f[8 * q + 2], f[8 * q + 3]),
-                                               pack_bf16(f[8 * q + 4], f[8 * q + 5]), pack_bf16(f[8 * q + 6], f[8 * q + 7]));
-                    }
+                    for (int j = 0; j < 4; ++j)
+                        if (bT0 + 8 * j < p.B) rr[j] = __ldg(reinterpret_cast<const uint4*>(p.res + (long long)(bT0 + 8 * j) * p.res_sb + res_base + c0 + 64));
                 }
             }
             tc_fence_before();
@@ -301,7 +310,7 @@ static int pick_bn(int OUT) {
 }
 
 static size_t tc_fixed_smem(int K, int bn) {   // everything except the A ring
-    return (size_t)(K / TC_BK) * bn * 128 + 2 * (size_t)bn * 4 + sizeof(TcBarriers) + 1024;
+    return (size_t)(K / TC_BK) * bn * 128 + 2 * (size_t)bn * 4 + (size_t)TC_EPI_WARPS * 32 * 32 * 4 + sizeof(TcBarriers) + 1024;
 }
 static int tc_stages(int K, int bn) {
     const size_t budget = 227 * 1024;
