@@ -206,6 +206,15 @@ glin_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 for (int j = 0; j < 4; ++j)
                     if (bT0 + 8 * j < p.B) rr[j] = __ldg(reinterpret_cast<const uint4*>(p.res + (long long)(bT0 + 8 * j) * p.res_sb + res_base + eg * 32));
             }
+            if (HAS_RES && it + 1 < item_hi) {
+                // one residual chunk per warp in flight does not cover DRAM latency (ncu: 38 % of the samples of the first capture
+                // were epilogue warps waiting for it): the NEXT tile's residual rows (half a row per thread) are pulled into L2 now
+                const long long it2 = it + 1, g2 = it2 / p.MT;
+                const int b2 = (int)(it2 % p.MT) * TC_BM + quarter * 32 + lane, node2 = (int)(g2 / p.NT), nt2 = (int)(g2 % p.NT);
+                if (b2 < p.B)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::
+                                 "l"(p.res + (long long)b2 * p.res_sb + (long long)node2 * p.res_sn + nt2 * p.BN + eg * (p.BN >> 1)), "r"((uint32_t)p.BN) : "memory");
+            }
             mbar_wait(&bars->acc_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (uint32_t)p.BN;
