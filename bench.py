@@ -218,6 +218,14 @@ def kernel_rooflines(dev, spec, diff, peaks):
     rl["reverse_step"] = {"kernel": "reverse_step_kernel<%d> (fused nonisotropic step, FFMA2), B=25600" % N, "bound": "hbm", "achieved": by / t / 1e9,
                           "peak": hbm, "unit": "GB/s", "frac": by / t / 1e9 / hbm, "traffic": traffic.get("reverse_step_kernel"), "ms": t * 1e3,
                           "bytes_per_sample_step": 4 * N * 96 * 4, "peak_source": src}
+    # (5) node attention (fp32, 8 heads x 32): reads q|k|v (768 floats) and writes 256 floats per (sample, node) row
+    qkv_t = torch.randn(B, N, 768, device=dev)
+    att_o = torch.empty(B, N, 256, device=dev)
+    t = _timed_kernel(dev, lambda: nv.check(lib.sd_node_attention(qkv_t.data_ptr(), att_o.data_ptr(), B, N, 8, 32, st), "sd_node_attention"))
+    by = B * N * (768 + 256) * 4.0
+    rl["node_attention"] = {"kernel": "node_attention_bulk_kernel<%d> (cp.async.bulk ring, FFMA2), fp32 I/O, B=25600" % N, "bound": "hbm",
+                            "achieved": by / t / 1e9, "peak": hbm, "unit": "GB/s", "frac": by / t / 1e9 / hbm,
+                            "traffic": traffic.get("node_attention_bulk_kernel"), "ms": t * 1e3, "bytes_per_sample": N * (768 + 256) * 4, "peak_source": src}
     return rl
 
 
