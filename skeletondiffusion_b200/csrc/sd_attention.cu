@@ -344,6 +344,172 @@ static int launch_attention_bulk(const float* qkv, float* out, int B, cudaStream
     return SD_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// bf16 I/O variant of the bulk pipeline (bf16 precision mode): same structure, a sample is N x 1536 B, a head's slice of a
+// row is 64 B = four 16-byte chunks of 8 bf16.  Rotation over 4 chunks (done on the packed words, before unpacking); with
+// 8 lanes per shared-memory phase two lanes share a bank group (2-way conflict) on the q load / output store only.
+constexpr int AB16_STAGES = 5;
+
+template <int DIR>
+__device__ __forceinline__ void ab_rotate4(uint4 (&x)[4], int n) {
+#pragma unroll
+    for (int r = 1; r < 4; r <<= 1) {
+        const bool on = (n & r) != 0;
+        uint4 t[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t[i] = x[(i + DIR * r) & 3];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            x[i].x = on ? t[i].x : x[i].x; x[i].y = on ? t[i].y : x[i].y;
+            x[i].z = on ? t[i].z : x[i].z; x[i].w = on ? t[i].w : x[i].w;
+        }
+    }
+}
+__device__ __forceinline__ float2 ab_unpack(uint32_t w) { return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u)); }
+__device__ __forceinline__ uint32_t ab_pack(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+
+struct __align__(8) Ab16Barriers { uint64_t full[AB16_STAGES], done[AB16_STAGES]; };
+
+template <int N>
+__global__ void __launch_bounds__(AB_THREADS, 1)
+node_attention_bulk_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int B) {
+    constexpr int ROW = 3 * AB_HEADS * AB_DH;                       // 768 bf16 per (sample, node) row
+    constexpr int IN_ELEMS = N * ROW, OUT_ROW = AB_HEADS * AB_DH, OUT_ELEMS = N * OUT_ROW;
+    constexpr uint32_t IN_BYTES = IN_ELEMS * 2u;
+    extern __shared__ __align__(128) float ab_smem[];
+    __nv_bfloat16* in_buf = reinterpret_cast<__nv_bfloat16*>(ab_smem);          // [AB16_STAGES][IN_ELEMS]
+    Ab16Barriers* bars = reinterpret_cast<Ab16Barriers*>(in_buf + AB16_STAGES * IN_ELEMS);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < AB16_STAGES; ++s) { tc::mbar_init(&bars->full[s], 1); tc::mbar_init(&bars->done[s], AB_HEADS); }
+        tc::fence_barrier_init();
+    }
+    __syncthreads();
+    const int my_samples = blockIdx.x < B ? (B - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    if (warp == AB_COPY_WARP) {
+        if (lane == 0) {
+            auto load = [&](int k) {
+                const int st = k % AB16_STAGES;
+                tc::mbar_arrive_expect_tx(&bars->full[st], IN_BYTES);
+                ab_bulk_load(in_buf + st * IN_ELEMS, qkv + ((long long)blockIdx.x + (long long)k * gridDim.x) * IN_ELEMS, IN_BYTES, &bars->full[st]);
+            };
+            for (int k = 0; k < AB16_STAGES && k < my_samples; ++k) load(k);
+            for (int k = 0; k < my_samples; ++k) {
+                const int st = k % AB16_STAGES;
+                tc::mbar_wait(&bars->done[st], (uint32_t)(k / AB16_STAGES) & 1u);
+                __nv_bfloat16* dst = out + ((long long)blockIdx.x + (long long)k * gridDim.x) * OUT_ELEMS;
+                const __nv_bfloat16* src = in_buf + st * IN_ELEMS;
+#pragma unroll 1
+                for (int r = 0; r < N; ++r) ab_bulk_store(dst + r * OUT_ROW, src + r * ROW, OUT_ROW * 2u);
+                ab_bulk_commit();
+                ab_bulk_wait_read();
+                if (k + AB16_STAGES < my_samples) load(k + AB16_STAGES);
+            }
+            ab_bulk_wait_all();
+        }
+        return;
+    }
+    const int h = warp % AB_HEADS, n = lane;
+    const bool active = n < N;
+    const float scale = rsqrtf((float)AB_DH);
+    int rot[4];                                                     // bf16 offset of the chunk visited at position i
+#pragma unroll
+    for (int i = 0; i < 4; ++i) rot[i] = 8 * ((i + n) & 3);
+    for (int k = 0; k < my_samples; ++k) {
+        const int stage = k % AB16_STAGES;
+        tc::mbar_wait(&bars->full[stage], (uint32_t)(k / AB16_STAGES) & 1u);
+        __nv_bfloat16* blk = in_buf + stage * IN_ELEMS + h * AB_DH;
+        if (active) {
+            __nv_bfloat16* qrow = blk + n * ROW;
+            float2 q[16];
+            {
+                uint4 qs[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) qs[i] = *reinterpret_cast<const uint4*>(qrow + rot[i]);
+                ab_rotate4<-1>(qs, n);                              // slot c = chunk c
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t w[4] = {qs[i].x, qs[i].y, qs[i].z, qs[i].w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 t = ab_unpack(w[e]);
+                        q[4 * i + e] = make_float2(t.x * scale, t.y * scale);    // q * dh^-1/2 (attention.py:128)
+                    }
+                }
+            }
+            float sc[N];
+            float mx = -INFINITY;
+            const __nv_bfloat16* kbase = blk + AB_HEADS * AB_DH;
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                float2 s2[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint4 kv = *reinterpret_cast<const uint4*>(kbase + j * ROW + 8 * i);          // broadcast
+                    att_ffma2(s2[0], q[4 * i + 0], ab_unpack(kv.x));
+                    att_ffma2(s2[1], q[4 * i + 1], ab_unpack(kv.y));
+                    att_ffma2(s2[2], q[4 * i + 2], ab_unpack(kv.z));
+                    att_ffma2(s2[3], q[4 * i + 3], ab_unpack(kv.w));
+                }
+                sc[j] = ((s2[0].x + s2[1].x) + (s2[2].x + s2[3].x)) + ((s2[0].y + s2[1].y) + (s2[2].y + s2[3].y));
+                mx = fmaxf(mx, sc[j]);
+            }
+            float2 acc[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) acc[c] = make_float2(0.f, 0.f);
+            float sum = 0.0f;
+            const __nv_bfloat16* vbase = blk + 2 * AB_HEADS * AB_DH;
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                const float pj = expf(sc[j] - mx);
+                sum += pj;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint4 vv = *reinterpret_cast<const uint4*>(vbase + j * ROW + 8 * i);          // broadcast
+                    att_ffma2s(acc[4 * i + 0], pj, ab_unpack(vv.x));
+                    att_ffma2s(acc[4 * i + 1], pj, ab_unpack(vv.y));
+                    att_ffma2s(acc[4 * i + 2], pj, ab_unpack(vv.z));
+                    att_ffma2s(acc[4 * i + 3], pj, ab_unpack(vv.w));
+                }
+            }
+            const float inv = 1.0f / sum;
+            uint4 os[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                os[i] = make_uint4(ab_pack(acc[4 * i].x * inv, acc[4 * i].y * inv), ab_pack(acc[4 * i + 1].x * inv, acc[4 * i + 1].y * inv),
+                                   ab_pack(acc[4 * i + 2].x * inv, acc[4 * i + 2].y * inv), ab_pack(acc[4 * i + 3].x * inv, acc[4 * i + 3].y * inv));
+            ab_rotate4<1>(os, n);                                   // slot i = chunk (i + n) & 3
+#pragma unroll
+            for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(qrow + rot[i]) = os[i];       // in place over this head's q slice
+        }
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&bars->done[stage]);
+    }
+}
+
+template <int N>
+static int launch_attention_bulk_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, cudaStream_t st) {
+    constexpr size_t smem = (size_t)(AB16_STAGES * N * 3) * AB_HEADS * AB_DH * sizeof(__nv_bfloat16) + sizeof(Ab16Barriers) + 128;
+    static_assert(smem <= 227 * 1024, "bf16 attention ring does not fit shared memory");
+    auto kern = node_attention_bulk_bf16_kernel<N>;
+    static bool configured = false;
+    if (!configured) {
+        SD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = B < sms ? B : sms;
+    kern<<<grid, AB_THREADS, smem, st>>>(qkv, out, B);
+    SD_LAUNCH_OK("node_attention_bulk_bf16_kernel");
+    return SD_OK;
+}
+
 static bool attention_legacy_forced() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("SKELDIFF_ATTENTION_LEGACY"); v = (e && e[0] == '1') ? 1 : 0; }
@@ -361,6 +527,17 @@ template <> struct BulkAttention<float> {
         if (N == 21) { *rc = launch_attention_bulk<21>(qkv, out, B, st); return true; }    // AMASS
         if (N == 16) { *rc = launch_attention_bulk<16>(qkv, out, B, st); return true; }    // H36M, README
         if (N == 17) { *rc = launch_attention_bulk<17>(qkv, out, B, st); return true; }    // FreeMan
+        return false;
+    }
+};
+
+template <> struct BulkAttention<__nv_bfloat16> {
+    static bool run(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int N, int heads, int dh, cudaStream_t st, int* rc) {
+        if (heads != AB_HEADS || dh != AB_DH || attention_legacy_forced()) return false;
+        if ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out)) & 15u) return false;
+        if (N == 21) { *rc = launch_attention_bulk_bf16<21>(qkv, out, B, st); return true; }
+        if (N == 16) { *rc = launch_attention_bulk_bf16<16>(qkv, out, B, st); return true; }
+        if (N == 17) { *rc = launch_attention_bulk_bf16<17>(qkv, out, B, st); return true; }
         return false;
     }
 };
