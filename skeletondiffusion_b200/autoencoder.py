@@ -158,6 +158,8 @@ class Decoder(nn.Module):
         if x.stride(-1) != 1:
             x = x.contiguous()
         B, N, _ = h.shape
+        if B == 0 or x.shape[0] == 0:       # empty batch: empty prediction, like the reference's loop over zero rows
+            return torch.empty(0, ph, N, self.fc.out_features, device=h.device, dtype=torch.float32), x[:, -1]
         if B % x.shape[0] != 0:
             raise ValueError("latent batch must be a multiple of the observation batch")
         rep = B // x.shape[0]

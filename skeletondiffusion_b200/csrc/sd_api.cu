@@ -334,6 +334,7 @@ size_t sd_denoiser_workspace_bytes(const sd_denoiser* d, int batch, int precisio
 
 int sd_denoiser_forward(const sd_denoiser* d, const sd_view* x, const sd_view* x_cond, const int32_t* t_rows_dev, int t_row,
                         float* out_dev, int batch, void* workspace_dev, int precision, void* stream) {
+    if (batch == 0) return SD_OK;   // an empty batch is a no-op (the reference returns empty tensors; zero-size device buffers have null pointers)
     if (!d || !x || !out_dev || !workspace_dev) { set_error("sd_denoiser_forward: null argument"); return SD_ERR_INVALID; }
     if (!d->time_table) { set_error("sd_denoiser_forward: time table not set"); return SD_ERR_INVALID; }
     if (!t_rows_dev && (t_row < 0 || t_row >= d->time_rows)) { set_error("sd_denoiser_forward: time row %d outside table of %d rows", t_row, d->time_rows); return SD_ERR_INVALID; }
@@ -437,6 +438,7 @@ void sd_diffusion_destroy(sd_diffusion* d) { delete d; }
 
 int sd_reverse_step(const sd_diffusion* d, const float* x_t_dev, const float* x0_dev, const sd_view* eps, float* x_out_dev,
                     float* mean_out_dev, int t, int batch, int clip_denoised, void* stream) {
+    if (batch == 0) return SD_OK;
     if (!d || !x_t_dev || !x0_dev || !x_out_dev) { set_error("sd_reverse_step: null argument"); return SD_ERR_INVALID; }
     if (x_out_dev == x_t_dev || x_out_dev == x0_dev) { set_error("sd_reverse_step: output must not alias an input"); return SD_ERR_INVALID; }
     View e = null_view();
@@ -467,6 +469,7 @@ size_t sd_sample_workspace_bytes(const sd_diffusion* df, const sd_denoiser* dn, 
 
 int sd_sample_loop(const sd_diffusion* df, const sd_denoiser* dn, float* x_dev, const sd_view* x_cond, const float* sampling_noise_dev,
                    float* means_out_dev, int batch, int clip_denoised, void* workspace_dev, int precision, void* stream) {
+    if (batch == 0) return SD_OK;
     if (!df || !dn || !x_dev || !workspace_dev) { set_error("sd_sample_loop: null argument"); return SD_ERR_INVALID; }
     if (df->N != dn->N || df->D != dn->dim || dn->out_dim != dn->dim) { set_error("sd_sample_loop: diffusion/denoiser shape mismatch"); return SD_ERR_INVALID; }
     if (dn->time_rows < df->T) { set_error("sd_sample_loop: time table has %d rows, need %d", dn->time_rows, df->T); return SD_ERR_INVALID; }
@@ -551,6 +554,7 @@ size_t sd_encode_workspace_bytes(int windows, int obs_len, int num_nodes, int hi
 int sd_encode(const sd_glin* initial_hidden, sd_gru* const* layers_host, int n_layers, const sd_glin* fc, const float* obs_dev,
               int windows, int obs_len, int feat, float* z_dev, int final_act, void* workspace_dev, int precision, void* stream) {
     (void)precision;   // the encoder runs once per window (1/num_samples of the work): fp32 path only
+    if (windows == 0) return SD_OK;
     if (!initial_hidden || !layers_host || n_layers <= 0 || !fc || !obs_dev || !z_dev || !workspace_dev) { set_error("sd_encode: null argument"); return SD_ERR_INVALID; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int W = windows, T = obs_len, N = initial_hidden->N, H = layers_host[0]->H;
@@ -633,6 +637,7 @@ size_t sd_decode_workspace_bytes(int batch, int num_nodes, int hidden) {
 
 int sd_decode(const sd_glin* initial_hidden, const sd_gru* cell, const sd_glin* fc, const sd_view* x_prev, const sd_view* x_last,
               const float* latent_dev, int batch, int ph, int feat, float* out_dev, void* workspace_dev, int precision, void* stream) {
+    if (batch == 0) return SD_OK;
     if (!initial_hidden || !cell || !fc || !x_prev || !x_last || !latent_dev || !out_dev || !workspace_dev) { set_error("sd_decode: null argument"); return SD_ERR_INVALID; }
     if (cell->steps < ph) { set_error("sd_decode: GRU plan has %d steps, ph=%d", cell->steps, ph); return SD_ERR_INVALID; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -192,6 +192,26 @@ def test_ragged_batches_match_oracle(cuda_device, batch):
     assert torch.isfinite(out).all()
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
+def test_empty_batch_returns_empty_tensors(cuda_device, precision):
+    """Zero windows / zero samples: the reference's modules return empty tensors of the right shape; so do the kernels'
+    wrappers (zero-size device buffers have null pointers: the C entry points treat batch == 0 as a no-op before any check)."""
+    import skeletondiffusion_b200 as sdb
+    spec = sdb.get_skeleton("h36m")
+    ae, diff = sdb.build_models(spec, cuda_device, precision=precision)
+    d, N = cuda_device, spec.num_nodes
+    x = torch.zeros(0, N, 96, device=d)
+    t = torch.zeros(0, dtype=torch.long, device=d)
+    obs = torch.zeros(0, spec.obs_length, N, 3, device=d)
+    assert tuple(diff.model(x, t, None, x, precision=precision).shape) == (0, N, 96)
+    assert tuple(diff.model.layers[0][0].block2.proj.plan().forward(torch.zeros(0, N, 192, device=d), precision=precision).shape) == (0, N, 192)
+    assert tuple(ae.get_past_embedding(obs).shape) == (0, N, 96)
+    assert tuple(ae.decode(obs, x, None, ph=5).shape) == (0, 5, N, 3)
+    assert tuple(diff.sample(batch_size=0, x_cond=x)[0].shape) == (0, N, 96)
+    pred = sdb.get_prediction(obs, (ae, diff), num_samples=4, pred_length=5, diffusion_conditioning=True)
+    assert tuple(pred.shape) == (0, 4, 5, N, 3)
+
+
 def test_full_size_batch_independence(cuda_device):
     """BASELINE eval geometry (512 windows x 50 samples = 25 600 latents): every row of the big batch must equal
     the same row sampled in a small batch (no cross-sample coupling), the t=0 output is clamped, and
