@@ -11,10 +11,15 @@
 // on the way into shared memory:
 //   warps 0-7  transform producers: coalesced LDG.128 of the fp32 tile rows (any sd_view: in-place repeat,
 //              two K segments), split, STS.64 into three SWIZZLE_128B K-major plane tiles, fence.proxy.async
-//   warp 12    TMEM allocator, TMA loads of the pre-split weight planes (resident per (node, n-tile) group), MMA issue
-//   warps 8-11 epilogue: tcgen05.ld (main + corr), row scale, bias, scale/shift, libdevice tanhf, fp32 residual, fp32 store
-// MMA-bound by construction: 6 x 2*K*OUT FLOP per row at the bf16 rate = the cost of an fp32-accurate GEMM
-// on a machine whose TF32 rate is half the bf16 rate.
+//   warps 8-11 epilogue: tcgen05.ld (main + corr), row scale, bias, scale/shift, libdevice tanhf, fp32 residual, fp32 store;
+//              16-column chunks transposed through a swizzled staging tile so that global accesses are coalesced
+//   warp 12    TMEM allocator, MMA issue; in the weight-resident schedule also the TMA of the weight planes
+//   warp 13    activation-stationary schedule only: streams (n-tile, k-block) weight planes through a two-slot TMA ring
+// Two schedules (weight-resident / activation-stationary) and the K-split of two-segment layers are described at the
+// places they are chosen (glin_tc3_launch, t3_launch_one).  Roofline: 6 x 2*K*OUT FLOP per row at the bf16 rate is
+// 0.14 ms for the 192 -> 192 layer at B = 25 600, the three fp32 streams (in, residual, out) are 0.19 ms of HBM time:
+// HBM is the binding floor; measured 0.28 ms bare / 0.46 ms with tanh + residual, where the four epilogue warps are
+// the limiter (profiles/README.md).
 //
 // Reference semantics: GraphLinear.forward, src/core/network/layers/graph_structural.py:30-43.
 #include "sd_internal.h"
