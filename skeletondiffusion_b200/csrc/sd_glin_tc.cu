@@ -9,10 +9,12 @@
 //   warp 1    MMA issuer: one elected lane issues tcgen05.mma.kind::f16 (M=128, N=BN, K=16) into one
 //             of two TMEM accumulator stages, tcgen05.commit releases smem stages / publishes the tile.
 //   warp 2    TMEM allocator (512 columns).
-//   warps 4-7 epilogue: tcgen05.ld (thread = sample row), row scale (RMSNorm fold), bias, time
-//             scale/shift, tanh, residual, bf16/fp32 store.
+//   warps 4-11 epilogue (two per TMEM lane quarter, alternating 32-column chunks): tcgen05.ld, row scale (RMSNorm
+//             fold), each chunk transposed through a swizzled fp32 staging tile so that four lanes cover one row;
+//             bias, time scale/shift, tanh, residual (coalesced, next tile's rows prefetched into L2), bf16/fp32 store.
 // The layer's arithmetic intensity (K = 192: 96 FLOP/B in bf16) is below the B200 ridge
-// (~209 FLOP/B), so the kernel is HBM-bound by design: its job is to stream activations once.
+// (~250 FLOP/B at the measured peaks), so the kernel is HBM-bound by design: its job is to stream activations once.
+// Measured: 0.163 ms for 192 -> 192 + tanh + residual at B = 25 600 = 58 % of the measured HBM peak.
 //
 // Reference semantics: GraphLinear.forward, src/core/network/layers/graph_structural.py:30-43.
 #include "sd_internal.h"
