@@ -191,3 +191,55 @@ def test_bf16x3_pipeline_meets_fp32_gate(cuda_device, name):
     pred = sdb.get_prediction(case["obs"].to(d), (ae, diff), num_samples=S, pred_length=ph, diffusion_conditioning=True,
                               sampler_kwargs=dict(start_noise=case["start_noise"].to(d), sampling_noise=case["sampling_noise"].to(d)))
     assert G.rel_err(pred.cpu(), case["pred"]) < 2e-4
+
+
+# ------------------------------------------------------------------------------------------------
+# determinism under repetition: the warp-specialised kernels order their shared-memory traffic with mbarriers only (TMA /
+# bulk-copy rings, in-place attention output, free-running warps); a missing ordering shows up as run-to-run differences.
+# Batches are several times the number of CTAs so that every ring wraps many times.  (compute-sanitizer is closed on the pool.)
+# ------------------------------------------------------------------------------------------------
+def test_pipelined_kernels_are_bitwise_repeatable(cuda_device):
+    import ctypes as C
+    import skeletondiffusion_b200 as sdb
+    from skeletondiffusion_b200 import _native as nv
+    from skeletondiffusion_b200.testing import synth_state_dict
+    d = cuda_device
+    spec = sdb.get_skeleton("amass")
+    N, nt = spec.num_nodes, spec.nodes_type_id
+    g = torch.Generator().manual_seed(11)
+    B = 2500                                                    # ~17 samples per CTA for the attention ring, 20 m-tiles per node
+    lib, st = nv.load(), nv.stream_ptr(d)
+
+    # (1) fp32 bulk attention, N = 21
+    qkv = torch.randn(B, N, 768, generator=g).to(d)
+    outs = []
+    for _ in range(12):
+        o = torch.empty(B, N, 256, device=d)
+        nv.check(lib.sd_node_attention(qkv.data_ptr(), o.data_ptr(), B, N, 8, 32, st), "sd_node_attention")
+        outs.append(o)
+    assert all(torch.equal(outs[0], o) for o in outs[1:])
+
+    # (2) bf16x3 graph-linears: activation-stationary 192 -> 768, K-split 384 -> 192, weight-resident 256 -> 192
+    for kin, kout, two_seg in ((192, 768, False), (384, 192, True), (256, 192, False)):
+        layer = sdb.StaticGraphLinear(kin, kout, bias=True, num_nodes=N, node_types=nt, learn_influence=True)
+        sd = synth_state_dict(layer.state_dict(), seed=kin + kout, mode="perturbed", gain=1.0)
+        sd["G"] = torch.eye(N)
+        layer.load_state_dict(sd)
+        plan = layer.to(d).plan()
+        a = torch.randn(B, N, 192 if two_seg else kin, generator=g).to(d)
+        b = torch.randn(B, N, 192, generator=g).to(d) if two_seg else None
+        res = torch.randn(B, N, kout, generator=g).to(d)
+        kw = dict(act=nv.ACT_TANH, precision="bf16x3") if two_seg else dict(act=nv.ACT_TANH, residual=res, precision="bf16x3")
+        first = plan.forward(a, x2=b, **kw).clone()
+        for _ in range(8):
+            assert torch.equal(first, plan.forward(a, x2=b, **kw))
+
+    # (3) bf16 Denoiser forward (tcgen05 bf16 kernels + bf16 bulk attention)
+    case = G.load_npz("amass_init")
+    _, _, diff, _, _ = G.dataset_models(case, device=d, precision="bf16")
+    x = torch.randn(B, N, 96, generator=g).to(d)
+    zp = torch.tanh(torch.randn(B // 50, N, 96, generator=g)).to(d)
+    t = torch.full((B,), 3, device=d)
+    first = diff.model(x, t, None, zp, precision="bf16").clone()
+    for _ in range(4):
+        assert torch.equal(first, diff.model(x, t, None, zp, precision="bf16"))
