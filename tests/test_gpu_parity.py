@@ -84,6 +84,27 @@ def test_node_attention_vs_oracle(cuda_device, N, heads, dh):
     assert G.rel_err(out.cpu(), ref) < FP32_TOL
 
 
+@pytest.mark.parametrize("N,B", [(21, 700), (16, 1001), (17, 149)])
+def test_bulk_attention_ring_wraps(cuda_device, N, B):
+    """The shipped configuration (8 heads x 32) runs the persistent bulk-copy kernel: one CTA per SM, samples grid-strided through
+    a 3-stage ring.  Batches larger than the CTA count (and not multiples of it) make every stage be loaded, computed on, stored
+    from and re-armed several times; every sample is checked against a plain fp32 softmax attention."""
+    nv = _native()
+    g = torch.Generator().manual_seed(N * 1000 + B)
+    heads, dh = 8, 32
+    qkv = torch.randn(B, N, 3 * heads * dh, generator=g)
+    q, k, v = [t.reshape(B, N, heads, dh).permute(0, 2, 1, 3) for t in qkv.chunk(3, -1)]
+    attn = torch.einsum("bhnc,bhjc->bhnj", q * dh ** -0.5, k).softmax(-1)
+    ref = torch.einsum("bhnj,bhjd->bhnd", attn, v).permute(0, 2, 1, 3).reshape(B, N, heads * dh)
+    qd = qkv.to(cuda_device)
+    out = torch.full((B, N, heads * dh), float("nan"), device=cuda_device)
+    nv.check(nv.load().sd_node_attention(qd.data_ptr(), out.data_ptr(), B, N, heads, dh, nv.stream_ptr(cuda_device)), "attn")
+    assert torch.isfinite(out).all()                            # every row of every sample was written
+    assert torch.equal(qd.cpu(), qkv)                           # the input is not modified (the in-place output lives in shared memory)
+    per_sample = (out.cpu() - ref).abs().amax(dim=(1, 2)) / ref.abs().amax()
+    assert float(per_sample.max()) < 1e-5
+
+
 @pytest.mark.parametrize("N,iso", [(21, False), (16, False), (17, False), (19, False), (21, True)])
 def test_reverse_step_vs_oracle(cuda_device, N, iso):
     """Templated (16/17/21), generic (19) and diagonal (U = I) variants; t = 0 must equal clamp(x0)."""
