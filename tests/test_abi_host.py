@@ -98,7 +98,7 @@ def test_cov_from_corr_matches_golden_and_isotropic_degenerate():
     case = G.load_npz("readme_perturbed")
     tabs = G.tables_of(case)
     s, l, u = sdb.get_cov_from_corr(case["corr"])
-    assert torch.allclose(s, tabs["Sigma_N"], atol=1e-6) and torch.allclose(l, tabs["Lambda_N"], atol=1e-6)
+    assert torch.allclose(s, tabs["Sigma_N"], atol=5e-6) and torch.allclose(l, tabs["Lambda_N"], atol=5e-6)
     assert torch.allclose((u * l) @ u.T, s, atol=1e-5)
     assert abs(float(l.max()) - 1.0) < 1e-6
     s, l, u = sdb.get_cov_from_corr(case["corr"], if_run_as_isotropic=True)
@@ -114,9 +114,19 @@ def test_diffusion_buffers_match_reference_tables():
         spec = sdb.get_skeleton(str(case["dataset"]))
         _, diff = sdb.build_models(spec, "cpu", if_run_as_isotropic=bool(case["iso"]))
         sd = diff.state_dict()
+        # Eigenvectors are defined up to sign and LAPACK's choice depends on the host CPU: bring the fixture's U to this
+        # host's signs (column j of U, hence row j of every "...mmUt" table and column j of every "Umm..." table), then
+        # compare.  fp32 eigh itself differs by a few ulp between hosts (1.1e-6 seen on Lambda_N = 2.4e-5 relative
+        # at the smallest eigenvalue 0.046, which the inverse-square-root tables inherit): 2e-5 of the table's scale.
+        sgn = torch.sign((sd["U"] * tabs["U"]).sum(0))
+        assert float(sgn.abs().min()) == 1.0
         for k, v in tabs.items():
             assert tuple(sd[k].shape) == tuple(v.shape), k
-            assert float((sd[k] - v).abs().max()) <= 1e-6, k
+            if k == "U" or k.startswith("Umm"):
+                v = v * sgn
+            elif k in ("U_transposed", "mahalanobis_S_sqrt_recip") or k.endswith("mmUt"):   # S_sqrt_recip = diag(.) U^T
+                v = v * sgn[:, None]
+            assert float((sd[k] - v).abs().max()) <= 2e-5 * max(1.0, float(v.abs().max())), k
 
 
 def test_shard_windows_partitions_exactly():
