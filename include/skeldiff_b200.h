@@ -211,6 +211,15 @@ int  sd_decode(const sd_glin* initial_hidden, const sd_gru* cell, const sd_glin*
                const sd_view* x_prev, const sd_view* x_last, const float* latent_dev, int batch,
                int ph, int feat, float* out_dev, void* workspace_dev, int precision, void* stream);
 
+/* ------------------------------------------------------------------ evaluation metrics ------
+ * replaces ade / fde / apd (src/metrics/multimodal.py:44-57, :60-73, :15-35) as eval.py applies them to
+ * skeleton.transform_to_metric_space(pred) (rescalepose.py:29-39; scale = pose_box_size, 1 for unit-box poses).
+ * pred_dev [W, S, T, feat], target_dev [W, T, feat] (feat = joints*3, contiguous); outputs [W] each, any may be NULL.
+ * ade = min_s mean_t ||pred - target||, fde = min_s ||.|| at the last frame, apd = mean pairwise distance of the S
+ * flattened samples (0 when S == 1).  S <= 91.  One launch, predictions read once. */
+int  sd_motion_metrics(const float* pred_dev, const float* target_dev, int windows, int samples, int frames, int feat,
+                       float scale, float* ade_dev, float* fde_dev, float* apd_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,5 +9,6 @@ from .autoencoder import AutoEncoder, Encoder, Decoder, StaticGraphGRU
 from .pipeline import (DiffusionManager, get_prediction, get_diffusion_latent_codes, decode_latent_pred,
                        shard_windows, build_models)
 from .skeletons import get_skeleton, SkeletonSpec
+from .metrics import motion_metrics, ade, fde, apd
 
 __version__ = "0.1.0"

@@ -67,6 +67,7 @@ SIGNATURES = {
     "sd_sample_workspace_bytes": (_SZ, [_P, _P, _I, _I]),
     "sd_sample_loop": (_I, [_P, _P, _P, C.POINTER(SdView), _P, _P, _I, _I, _P, _I, _P]),
     "sd_fill_normal": (_I, [_P, _I64, _U64, _U64, _P]),
+    "sd_motion_metrics": (_I, [_P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P]),
     "sd_gru_create": (_I, [_I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, C.POINTER(_P)]),
     "sd_gru_set_fused": (_I, [_P, _P, _P, _P, _P]),
     "sd_gru_destroy": (None, [_P]),

@@ -461,6 +461,14 @@ int sd_fill_normal(float* out_dev, int64_t count, uint64_t seed, uint64_t offset
     return fill_normal(out_dev, count, seed, offset, static_cast<cudaStream_t>(stream));
 }
 
+int sd_motion_metrics(const float* pred_dev, const float* target_dev, int windows, int samples, int frames, int feat,
+                      float scale, float* ade_dev, float* fde_dev, float* apd_dev, void* stream) {
+    if (windows == 0) return SD_OK;
+    if (windows < 0 || samples < 1 || frames < 1 || feat < 1) { set_error("sd_motion_metrics: bad shape [%d, %d, %d, %d]", windows, samples, frames, feat); return SD_ERR_INVALID; }
+    if (!pred_dev || !target_dev || !(ade_dev || fde_dev || apd_dev)) { set_error("sd_motion_metrics: null argument"); return SD_ERR_INVALID; }
+    return motion_metrics_fp32(pred_dev, target_dev, windows, samples, frames, feat, scale, ade_dev, fde_dev, apd_dev, static_cast<cudaStream_t>(stream));
+}
+
 size_t sd_sample_workspace_bytes(const sd_diffusion* df, const sd_denoiser* dn, int batch, int precision) {
     if (!df || !dn || batch <= 0) return 0;
     const size_t lat = align_up((size_t)batch * df->N * df->D * sizeof(float));

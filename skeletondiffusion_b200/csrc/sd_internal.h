@@ -67,6 +67,8 @@ int time_table_fp32(const float* times, int rows, int C, float theta, int time_d
                     const float* w3, const float* b3, const float* const* head_w, const float* const* head_b,
                     int n_heads, float* table, float* ws, cudaStream_t st);
 int fill_normal(float* out, long long count, uint64_t seed, uint64_t offset, cudaStream_t st);
+int motion_metrics_fp32(const float* pred, const float* target, int windows, int samples, int frames, int feat, float scale,
+                        float* ade, float* fde, float* apd, cudaStream_t st);
 int q_sample_fp32(const float* x0, const float* eps, const int* t, const float* sqrt_ac, const float* M, float* out,
                   int B, int N, int D, cudaStream_t st);
 int mahalanobis_loss_fp32(const float* out, const float* x0, const int* t, const float* S, float* loss,
