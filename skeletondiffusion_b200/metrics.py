@@ -7,6 +7,7 @@ that all three metrics are linear in: pass it as `scale` to `motion_metrics` ins
 prediction tensor.  CUDA only: there is no CPU fallback (the CPU statement of the metrics lives in the test infrastructure)."""
 from __future__ import annotations
 
+import math
 from typing import Optional, Tuple
 
 import torch
@@ -29,17 +30,18 @@ def motion_metrics(target: Optional[torch.Tensor], pred: torch.Tensor, scale: fl
     want_ade, want_fde, want_apd = want
     pred = _frames(pred, t0, t, 2)
     W, S, T = pred.shape[:3]
-    p = pred.reshape(W, S, T, -1).to(torch.float32).contiguous()
-    F = p.shape[-1]
+    F = math.prod(pred.shape[3:])
+    p = pred.reshape(W, S, T, F).to(torch.float32).contiguous()
     if target is None:
         if want_ade or want_fde:
             raise ValueError("ADE / FDE need a target")
         tg = p[:, 0]                                   # read but unused by the APD result
     else:
         nv.require_cuda(target, "target")
-        tg = _frames(target, t0, t, 1).reshape(W, T, -1).to(torch.float32).contiguous()
-        if tuple(tg.shape) != (W, T, F):
+        tg = _frames(target, t0, t, 1)
+        if tg.shape[0] != W or tg.shape[1] != T or math.prod(tg.shape[2:]) != F:
             raise ValueError(f"target {tuple(target.shape)} does not match pred {tuple(pred.shape)}")
+        tg = tg.reshape(W, T, F).to(torch.float32).contiguous()
     outs = [torch.empty(W, device=p.device, dtype=torch.float32) if w else None for w in (want_ade, want_fde, want_apd)]
     if W and T and F:
         nv.check(nv.load().sd_motion_metrics(p.data_ptr(), tg.data_ptr(), W, S, T, F, float(scale),
