@@ -7,23 +7,23 @@
 // exactly once, a few frames at a time, into shared memory ([S][frames*F] with an odd row stride, so lanes that walk
 // different samples hit different banks).  While a chunk is resident
 //   - thread s accumulates ||pred[s, f] - target[f]|| of its frames (ADE sum, FDE = last frame),
-//   - every thread accumulates the squared distance of its share of the S(S-1)/2 sample pairs (APD).
+//   - the S x S pair matrix (APD) is accumulated in 5 x 5 register tiles: 10 shared-memory loads per 25 pairs and column.
 // Reductions are fixed-order (one owner per sample / pair, tree sum), so results are bitwise repeatable.
-// Algorithmic bytes per window: 4*(S+1)*T*F read + 12 written.  The pair loop is shared-memory-bandwidth bound
-// (two LDS per FMA), not HBM bound: see DESIGN.md 4.7.
+// Algorithmic bytes per window: 4*(S+1)*T*F read + 12 written.  See DESIGN.md 4.7.
 #include "sd_internal.h"
 
 namespace sd {
 
 constexpr int MM_THREADS = 256;
-constexpr int MM_PMAX    = 16;     // pairs per thread: S(S-1)/2 <= 4096, i.e. S <= 91
+constexpr int MM_TB      = 5;      // edge of a register tile of sample pairs
+constexpr int MM_SMAX    = 91;     // 19 x 20 / 2 = 190 tiles <= MM_THREADS
 
-__global__ void __launch_bounds__(MM_THREADS)
+__global__ void __launch_bounds__(MM_THREADS, 4)
 motion_metrics_kernel(const float* __restrict__ pred, const float* __restrict__ target, int S, int T, int F, int fc, int stride,
-                      float scale, float* __restrict__ ade, float* __restrict__ fde, float* __restrict__ apd) {
+                      int row_floats, float scale, float* __restrict__ ade, float* __restrict__ fde, float* __restrict__ apd) {
     extern __shared__ float sm[];
     float* rows  = sm;                          // [S][stride]
-    float* tgt   = rows + (size_t)S * stride;   // [fc*F]
+    float* tgt   = rows + row_floats;           // [fc*F]
     float* asum  = tgt + fc * F;                // [S] sum over frames of the per-frame distance
     float* flast = asum + S;                    // [S] distance at the last frame
     float* red   = flast + S;                   // [MM_THREADS]
@@ -33,17 +33,24 @@ motion_metrics_kernel(const float* __restrict__ pred, const float* __restrict__ 
     const float* tw = target + (long long)w * D;
     const int pairs = S * (S - 1) / 2;
 
-    int oi[MM_PMAX], oj[MM_PMAX];
-    float acc[MM_PMAX];
+    // APD: the S x S pair matrix is cut into MM_TB x MM_TB register tiles (upper triangle, diagonal tiles included);
+    // thread (tile, q) owns the tile's 25 accumulators for the columns c = q, q + Q, ...  Lanes of a warp hold different
+    // tiles and the same q: their rows differ by multiples of MM_TB, which an odd row stride spreads over distinct banks.
+    const int nb = (S + MM_TB - 1) / MM_TB, ntiles = nb * (nb + 1) / 2;
+    const int Q = max(1, MM_THREADS / ntiles);
+    const int tile = tid % ntiles, q = tid / ntiles;
+    const bool pair_thread = q < Q;
+    int tI = 0, tJ = tile;
+    while (tJ >= nb - tI) { tJ -= nb - tI; ++tI; }
+    tJ += tI;
+    int ra[MM_TB], rb[MM_TB];
+    float acc[MM_TB][MM_TB];
 #pragma unroll
-    for (int k = 0; k < MM_PMAX; ++k) {
-        acc[k] = 0.f; oi[k] = oj[k] = 0;
-        int p = tid + k * MM_THREADS;
-        if (p < pairs) {                        // row-major upper triangle: p -> (i, j), i < j
-            int i = 0;
-            while (p >= S - 1 - i) { p -= S - 1 - i; ++i; }
-            oi[k] = i * stride; oj[k] = (i + 1 + p) * stride;
-        }
+    for (int u = 0; u < MM_TB; ++u) {
+        ra[u] = min(tI * MM_TB + u, S - 1) * stride;
+        rb[u] = min(tJ * MM_TB + u, S - 1) * stride;
+#pragma unroll
+        for (int v = 0; v < MM_TB; ++v) acc[u][v] = 0.f;
     }
     for (int s = tid; s < S; s += MM_THREADS) { asum[s] = 0.f; flast[s] = 0.f; }
 
@@ -69,26 +76,43 @@ motion_metrics_kernel(const float* __restrict__ pred, const float* __restrict__ 
             }
             asum[s] = a;
         }
+        if (pair_thread) {
+            for (int c = q; c < len; c += Q) {
+                float av[MM_TB], bv[MM_TB];
 #pragma unroll
-        for (int k = 0; k < MM_PMAX; ++k) {
-            if (tid + k * MM_THREADS < pairs) {
-                const float* a = rows + oi[k];
-                const float* b = rows + oj[k];
-                float s0 = 0.f, s1 = 0.f;
-                int c = 0;
-                for (; c + 1 < len; c += 2) {
-                    const float d0 = a[c] - b[c], d1 = a[c + 1] - b[c + 1];
-                    s0 = fmaf(d0, d0, s0); s1 = fmaf(d1, d1, s1);
-                }
-                if (c < len) { const float d0 = a[c] - b[c]; s0 = fmaf(d0, d0, s0); }
-                acc[k] += s0 + s1;
+                for (int u = 0; u < MM_TB; ++u) { av[u] = rows[ra[u] + c]; bv[u] = rows[rb[u] + c]; }
+#pragma unroll
+                for (int u = 0; u < MM_TB; ++u)
+#pragma unroll
+                    for (int v = 0; v < MM_TB; ++v) { const float d = av[u] - bv[v]; acc[u][v] = fmaf(d, d, acc[u][v]); }
             }
         }
     }
 
-    float local = 0.f;
+    // column shares of a tile are added in the order q = 0, 1, ... by the tile's first thread (fixed order)
+    __syncthreads();
+    float* part = rows;                         // [MM_THREADS][MM_TB*MM_TB], the sample rows are no longer needed
+    if (pair_thread) {
 #pragma unroll
-    for (int k = 0; k < MM_PMAX; ++k) if (tid + k * MM_THREADS < pairs) local += sqrtf(acc[k]);
+        for (int u = 0; u < MM_TB; ++u)
+#pragma unroll
+            for (int v = 0; v < MM_TB; ++v) part[tid * (MM_TB * MM_TB) + u * MM_TB + v] = acc[u][v];
+    }
+    __syncthreads();
+    float local = 0.f;
+    if (q == 0) {
+#pragma unroll
+        for (int u = 0; u < MM_TB; ++u)
+#pragma unroll
+            for (int v = 0; v < MM_TB; ++v) {
+                const int i = tI * MM_TB + u, j = tJ * MM_TB + v;
+                if (i < j && j < S) {
+                    float d2 = 0.f;
+                    for (int qq = 0; qq < Q; ++qq) d2 += part[(tile + qq * ntiles) * (MM_TB * MM_TB) + u * MM_TB + v];
+                    local += sqrtf(d2);
+                }
+            }
+    }
     red[tid] = local;
     __syncthreads();
     for (int h = MM_THREADS / 2; h > 0; h >>= 1) {
@@ -107,16 +131,18 @@ motion_metrics_kernel(const float* __restrict__ pred, const float* __restrict__ 
 int motion_metrics_fp32(const float* pred, const float* target, int windows, int samples, int frames, int feat, float scale,
                         float* ade, float* fde, float* apd, cudaStream_t st) {
     const int S = samples, T = frames, F = feat;
-    if (S * (S - 1) / 2 > MM_PMAX * MM_THREADS) { set_error("sd_motion_metrics: at most 91 samples per window (got %d)", S); return SD_ERR_UNSUPPORTED; }
+    if (S > MM_SMAX) { set_error("sd_motion_metrics: at most 91 samples per window (got %d)", S); return SD_ERR_UNSUPPORTED; }
     // frames per chunk: as many as keep the sample rows within 40 KB (5 CTAs per SM); one frame at least
     int fc = (40 * 1024 / 4) / (S * F);
     fc = fc < 1 ? 1 : (fc > T ? T : fc);
     const int stride = (fc * F) | 1;
-    const size_t smem = ((size_t)S * stride + (size_t)fc * F + 2 * (size_t)S + MM_THREADS) * sizeof(float);
+    size_t row_floats = (size_t)S * stride;                                    // reused for the tiles' partial sums at the end
+    if (row_floats < (size_t)MM_THREADS * MM_TB * MM_TB) row_floats = (size_t)MM_THREADS * MM_TB * MM_TB;
+    const size_t smem = (row_floats + (size_t)fc * F + 2 * (size_t)S + MM_THREADS) * sizeof(float);
     if (smem > 200 * 1024) { set_error("sd_motion_metrics: one frame of %d samples x %d features does not fit shared memory", S, F); return SD_ERR_UNSUPPORTED; }
     if (smem > 48 * 1024 &&
         check_cuda(cudaFuncSetAttribute(motion_metrics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "motion_metrics smem")) return SD_ERR_CUDA;
-    motion_metrics_kernel<<<windows, MM_THREADS, smem, st>>>(pred, target, S, T, F, fc, stride, scale, ade, fde, apd);
+    motion_metrics_kernel<<<windows, MM_THREADS, smem, st>>>(pred, target, S, T, F, fc, stride, (int)row_floats, scale, ade, fde, apd);
     SD_LAUNCH_OK("motion_metrics_kernel");
     return SD_OK;
 }
