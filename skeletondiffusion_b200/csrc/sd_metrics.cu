@@ -6,7 +6,8 @@
 // One CTA per window.  The window's S predictions [S, T, F] (AMASS: 50 x 120 x 63 floats = 1.5 MB) are read from HBM
 // exactly once, a few frames at a time, into shared memory ([S][frames*F] with an odd row stride, so lanes that walk
 // different samples hit different banks).  While a chunk is resident
-//   - thread s accumulates ||pred[s, f] - target[f]|| of its frames (ADE sum, FDE = last frame),
+//   - one thread per (sample, frame) computes ||pred[s, f] - target[f]||; sample s's owner adds them in frame order
+//     (ADE sum, FDE = last frame),
 //   - the S x S pair matrix (APD) is accumulated in 5 x 5 register tiles: 10 shared-memory loads per 25 pairs and column.
 // Reductions are fixed-order (one owner per sample / pair, tree sum), so results are bitwise repeatable.
 // Algorithmic bytes per window: 4*(S+1)*T*F read + 12 written.  See DESIGN.md 4.7.
@@ -27,6 +28,7 @@ motion_metrics_kernel(const float* __restrict__ pred, const float* __restrict__ 
     float* asum  = tgt + fc * F;                // [S] sum over frames of the per-frame distance
     float* flast = asum + S;                    // [S] distance at the last frame
     float* red   = flast + S;                   // [MM_THREADS]
+    float* fd    = red + MM_THREADS;            // [S][fc] per-frame distances of the resident chunk
     const int w = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long D = (long long)T * F;
     const float* pw = pred + (long long)w * S * D;
@@ -54,27 +56,40 @@ motion_metrics_kernel(const float* __restrict__ pred, const float* __restrict__ 
     }
     for (int s = tid; s < S; s += MM_THREADS) { asum[s] = 0.f; flast[s] = 0.f; }
 
-    for (int f0 = 0; f0 < T; f0 += fc) {
+    for (int f0 = 0; ; f0 += fc) {              // one extra turn (f0 >= T) folds the last chunk's frame distances
         const int nf = min(fc, T - f0), len = nf * F;
         __syncthreads();                        // previous chunk fully consumed (and asum initialised)
+        if (f0 > 0) {                           // sample s adds the previous chunk's frames in frame order (fixed order)
+            const int pf = min(fc, T - (f0 - fc));
+            for (int s = tid; s < S; s += MM_THREADS) {
+                float a = asum[s];
+                for (int f = 0; f < pf; ++f) a += fd[s * fc + f];
+                asum[s] = a;
+                if (f0 >= T) flast[s] = fd[s * fc + pf - 1];
+            }
+        }
+        if (f0 >= T) break;
+        // rows are only 4-byte aligned (F = 63): 4-byte asynchronous copies, all of a thread's loads in flight at once
         for (int s = warp; s < S; s += MM_THREADS / 32) {
             const float* src = pw + s * D + (long long)f0 * F;
-            float* dst = rows + (size_t)s * stride;
-            for (int c = lane; c < len; c += 32) dst[c] = __ldg(src + c);
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(rows + (size_t)s * stride);
+            for (int c = lane; c < len; c += 32)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst + 4u * c), "l"(src + c) : "memory");
         }
-        for (int c = tid; c < len; c += MM_THREADS) tgt[c] = __ldg(tw + (long long)f0 * F + c);
+        {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(tgt);
+            for (int c = tid; c < len; c += MM_THREADS)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst + 4u * c), "l"(tw + (long long)f0 * F + c) : "memory");
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
         __syncthreads();
-        for (int s = tid; s < S; s += MM_THREADS) {
-            const float* r = rows + (size_t)s * stride;
-            float a = asum[s];
-            for (int f = 0; f < nf; ++f) {
-                float d2 = 0.f;
-                for (int c = 0; c < F; ++c) { const float d = r[f * F + c] - tgt[f * F + c]; d2 = fmaf(d, d, d2); }
-                const float dist = sqrtf(d2);
-                a += dist;
-                if (f0 + f == T - 1) flast[s] = dist;
-            }
-            asum[s] = a;
+        for (int task = tid; task < S * nf; task += MM_THREADS) {       // one (sample, frame) distance per thread
+            const int s = task / nf, f = task - s * nf;
+            const float* r = rows + (size_t)s * stride + f * F;
+            const float* g = tgt + f * F;
+            float d2 = 0.f;
+            for (int c = 0; c < F; ++c) { const float d = r[c] - g[c]; d2 = fmaf(d, d, d2); }
+            fd[s * fc + f] = sqrtf(d2);
         }
         if (pair_thread) {
             for (int c = q; c < len; c += Q) {
@@ -138,7 +153,7 @@ int motion_metrics_fp32(const float* pred, const float* target, int windows, int
     const int stride = (fc * F) | 1;
     size_t row_floats = (size_t)S * stride;                                    // reused for the tiles' partial sums at the end
     if (row_floats < (size_t)MM_THREADS * MM_TB * MM_TB) row_floats = (size_t)MM_THREADS * MM_TB * MM_TB;
-    const size_t smem = (row_floats + (size_t)fc * F + 2 * (size_t)S + MM_THREADS) * sizeof(float);
+    const size_t smem = (row_floats + (size_t)fc * F + 2 * (size_t)S + MM_THREADS + (size_t)S * fc) * sizeof(float);
     if (smem > 200 * 1024) { set_error("sd_motion_metrics: one frame of %d samples x %d features does not fit shared memory", S, F); return SD_ERR_UNSUPPORTED; }
     if (smem > 48 * 1024 &&
         check_cuda(cudaFuncSetAttribute(motion_metrics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "motion_metrics smem")) return SD_ERR_CUDA;
