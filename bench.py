@@ -226,6 +226,19 @@ def kernel_rooflines(dev, spec, diff, peaks):
     rl["node_attention"] = {"kernel": "node_attention_bulk_kernel<%d> (cp.async.bulk ring, FFMA2), fp32 I/O, B=25600" % N, "bound": "hbm",
                             "achieved": by / t / 1e9, "peak": hbm, "unit": "GB/s", "frac": by / t / 1e9 / hbm,
                             "traffic": traffic.get("node_attention_bulk_kernel"), "ms": t * 1e3, "bytes_per_sample": N * (768 + 256) * 4, "peak_source": src}
+    del qkv_t, att_o, x, res, out
+    # (6) evaluation metrics right after the path (ADE / FDE / APD per window): reads the 512 x 50 predictions and the targets once
+    W, S, T, F = 512, 50, 120, N * 3
+    pred_m = torch.rand(W, S, T, F, device=dev) * 2 - 1
+    tgt_m = torch.rand(W, T, F, device=dev) * 2 - 1
+    m_out = torch.empty(3, W, device=dev)
+    t = _timed_kernel(dev, lambda: nv.check(lib.sd_motion_metrics(pred_m.data_ptr(), tgt_m.data_ptr(), W, S, T, F, 1.5, m_out[0].data_ptr(),
+                                                                  m_out[1].data_ptr(), m_out[2].data_ptr(), st), "sd_motion_metrics"))
+    by = 4.0 * (S + 1) * T * F * W + 12 * W
+    rl["motion_metrics"] = {"kernel": "motion_metrics_kernel (ADE/FDE/APD, 5x5 register tiles of sample pairs), 512 windows x 50 samples", "bound": "hbm",
+                            "achieved": by / t / 1e9, "peak": hbm, "unit": "GB/s", "frac": by / t / 1e9 / hbm,
+                            "traffic": traffic.get("motion_metrics_kernel"), "ms": t * 1e3, "bytes_per_window": 4 * (S + 1) * T * F + 12,
+                            "note": "FP32-issue bound, not HBM bound (DESIGN.md 4.7)", "peak_source": src}
     return rl
 
 
