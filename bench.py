@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--cpu-windows", type=int, default=64, help="windows of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--perturbed", action="store_true", help="dense non-identity graph-influence matrices (trained-model-like)")
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference only: cpu = the reference arm (host cores); cuda = the same stock eager code on the GPU")
     return ap.parse_args()
 
 
@@ -120,31 +122,103 @@ def cpu_reference_time(spec, ae, diff, windows, samples, repeats=1):
     return B / best, best
 
 
+NUM_JOINTS = {"amass": 22, "h36m": 17, "freeman": 18}
+
+
+def reference_models(spec, dataset, perturbed, device):
+    """The UNMODIFIED reference classes from oracle/_ref (copied there by oracle/make_ref.py), dataset configuration, reference
+    initialisation under torch.manual_seed(0) (configs/config_eval).  Returns (autoencoder, diffusion, get_prediction)."""
+    import contextlib
+    import warnings
+    warnings.filterwarnings("ignore")
+    with contextlib.redirect_stdout(sys.stderr):      # the reference prints while it builds its modules; stdout carries the JSON line only
+        return _reference_models(spec, dataset, perturbed, device)
+
+
+def _reference_models(spec, dataset, perturbed, device):
+    from src.core import AutoEncoder as RefAutoEncoder, DiffusionManager as RefDiffusionManager
+    from src.data.skeleton import create_skeleton
+    from src.eval_prepare_model import get_prediction as ref_get_prediction
+    torch.manual_seed(0)
+    sk = create_skeleton(dataset_name=dataset, motion_repr_type="SkeletonRescalePose", num_joints=NUM_JOINTS[dataset], if_consider_hip=False,
+                         obs_length=spec.obs_length, pred_length=spec.pred_length, pose_box_size=spec.pose_box_size)
+    arch = dict(depth=4, attn_heads=8, attn_dim_head=32, use_attention=True, self_condition=False, norm_type="none", learn_influence=True)
+    mgr = RefDiffusionManager(diffusion_type="NonisotropicGaussianDiffusion", skeleton=sk, covariance_matrix_type="adjacency",
+                              num_nodes=sk.num_nodes, node_types=sk.nodes_type_id, diffusion_conditioning=True, latent_size=96,
+                              diffusion_timesteps=10, diffusion_objective="pred_x0", beta_schedule="cosine", diffusion_arch=arch)
+    diff = mgr.get_diffusion()
+    ae = RefAutoEncoder(num_nodes=sk.num_nodes, encoder_hidden_size=96, decoder_hidden_size=96, latent_size=96, node_types=sk.nodes_type_id,
+                        input_size=3, z_activation="tanh", enc_num_layers=spec.enc_num_layers, recurrent_arch_enc="StaticGraphGRU",
+                        recurrent_arch_decoder="StaticGraphGRU", output_size=3, if_consider_hip=False)
+    if perturbed:
+        from skeletondiffusion_b200.testing import synth_state_dict
+        diff.load_state_dict(synth_state_dict(diff.state_dict(), seed=1, mode="perturbed", gain=2.5))
+        ae.load_state_dict(synth_state_dict(ae.state_dict(), seed=2, mode="perturbed", gain=2.5))
+    return ae.to(device).eval(), diff.to(device).eval(), ref_get_prediction
+
+
+def reference_time(spec, ae, diff, get_pred, windows, samples, device):
+    """One timed call of the reference's own get_prediction (src/eval_prepare_model.py:118-121) on `windows` windows."""
+    obs = synthetic_obs(spec, windows, 123).to(device)
+    with torch.no_grad():
+        if device.type == "cuda":
+            torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        pred = get_pred(obs, (ae, diff), num_samples=samples, pred_length=spec.pred_length, diffusion_conditioning=True)
+        if device.type == "cuda":
+            torch.cuda.synchronize(device)
+        dt = time.perf_counter() - t0
+    assert tuple(pred.shape) == (windows, samples, spec.pred_length, spec.num_nodes, 3)
+    return dt
+
+
 def run_reference(args):
+    """Reference arm: the reference's own implementation of the path on the host cores (all threads), a bounded sample of the
+    workload per step.  oracle/_ref (the unmodified reference package, see oracle/make_ref.py) when present -> kind "reference";
+    otherwise the oracle port -> kind "port".  --ref-device cuda times the same stock eager PyTorch code on the GPU instead
+    (the like-for-like GPU comparison of SURVEY 8d; reported under its own key, never as the CPU baseline)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import skeletondiffusion_b200 as sdb
+    from oracle import make_ref
     spec = sdb.get_skeleton(args.dataset)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    ae, diff = oracle_state(spec, args.perturbed)
     w = max(1, args.cpu_windows)
-    cpu_reference_time(spec, ae, diff, 1, args.samples)       # warm-up (thread pools, allocator)
-    times = []
-    for _ in range(max(1, min(args.steps, 3))):
-        v, dt = cpu_reference_time(spec, ae, diff, w, args.samples)
-        times.append(dt)
+    steps, warm = max(1, args.steps), max(1, min(args.warmup, 1))
+    have_ref = make_ref.add_to_path()
+    on_gpu = args.ref_device == "cuda"
+    if on_gpu and not have_ref:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref is absent: run python oracle/make_ref.py in the build container"}))
+        return
+    if have_ref:
+        device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))) if on_gpu else torch.device("cpu")
+        ae, diff, get_pred = reference_models(spec, args.dataset, args.perturbed, device)
+        for _ in range(warm):
+            reference_time(spec, ae, diff, get_pred, 1 if not on_gpu else w, args.samples, device)
+        times = [reference_time(spec, ae, diff, get_pred, w, args.samples, device) for _ in range(min(steps, 5 if on_gpu else 3))]
+        kind = "reference"
+        what = f"{w} windows x {args.samples} samples, unmodified reference get_prediction (oracle/_ref, src/eval_prepare_model.py:118-121), torch {torch.__version__} {'CUDA eager' if on_gpu else 'CPU'} fp32"
+    else:
+        ae, diff = oracle_state(spec, args.perturbed)
+        cpu_reference_time(spec, ae, diff, 1, args.samples)       # warm-up (thread pools, allocator)
+        times = [cpu_reference_time(spec, ae, diff, w, args.samples)[1] for _ in range(min(steps, 3))]
+        kind = "port"
+        what = f"{w} windows x {args.samples} samples, oracle/skeldiff_oracle.py get_prediction, torch {torch.__version__} CPU fp32"
     dt = sum(times) / len(times)
     value = w * args.samples / dt
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
-            "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic observations, random-init weights",
+            "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic observations, random-init weights" + (" with dense perturbed graph-influence matrices" if args.perturbed else ""),
             "config": {"workload": f"{args.dataset} eval: {w} windows x {args.samples} samples per step (bounded sample of the 512-window batch)",
-                       "windows_per_step": w, "samples": args.samples, "timesteps": 10, "pred_length": spec.pred_length},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{w} windows x {args.samples} samples, oracle/skeldiff_oracle.py get_prediction, torch {torch.__version__} CPU fp32"},
+                       "windows_per_step": w, "samples": args.samples, "timesteps": 10, "pred_length": spec.pred_length,
+                       "device": "cuda (stock eager PyTorch)" if on_gpu else "cpu"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if on_gpu:
+        line["reference_gpu_eager"] = {"value": value, "unit": UNIT, "kind": kind, "sample": what, "device": torch.cuda.get_device_name(0)}
+    else:
+        line["cpu_baseline"] = {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": what}
     print(json.dumps(line))
 
 
@@ -205,8 +279,10 @@ def kernel_rooflines(dev, spec, diff, peaks):
     # (3) bf16 graph-linear on its native bf16 tensors: K = 192 -> 96 FLOP/B, below the ridge => HBM-bound
     x16, r16, o16 = x.to(torch.bfloat16), res.to(torch.bfloat16), torch.empty(B, N, C, device=dev, dtype=torch.bfloat16)
     st = nv.stream_ptr(dev)
+    scr16 = None if plan.identity else torch.empty(B, N, C, device=dev)      # raw products of a layer with a dense graph influence
     t = _timed_kernel(dev, lambda: nv.check(lib.sd_glin_forward_bf16(plan.handle, x16.data_ptr(), None, ss.data_ptr(), nv.ACT_TANH, r16.data_ptr(),
-                                                                     o16.data_ptr(), 0, None, B, st), "sd_glin_forward_bf16"))
+                                                                     o16.data_ptr(), 0, nv.dptr(scr16), B, st), "sd_glin_forward_bf16"))
+    del scr16
     by = B * N * C * 2 * 3.0
     rl["glin_tc_bf16"] = {"kernel": "glin_tc_kernel (tcgen05/TMEM/TMA): same layer, bf16 activations", "bound": "hbm", "achieved": by / t / 1e9,
                           "peak": hbm, "unit": "GB/s", "frac": by / t / 1e9 / hbm, "traffic": traffic.get("glin_tc_kernel"), "ms": t * 1e3,
@@ -350,10 +426,19 @@ def run_ours(args):
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        cpu_reference_time(spec, ae_cpu, diff_cpu, 1, S)
-        v, dt = cpu_reference_time(spec, ae_cpu, diff_cpu, args.cpu_windows, S)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"{args.cpu_windows} windows x {S} samples ({dt:.1f} s), oracle port of the reference algorithm, torch CPU fp32"}
+        from oracle import make_ref
+        if make_ref.add_to_path():     # the unmodified reference package (oracle/_ref), timed as itself on the host cores
+            cpu = torch.device("cpu")
+            r_ae, r_diff, r_pred = reference_models(spec, args.dataset, args.perturbed, cpu)
+            reference_time(spec, r_ae, r_diff, r_pred, 1, S, cpu)
+            dt = reference_time(spec, r_ae, r_diff, r_pred, args.cpu_windows, S, cpu)
+            line["cpu_baseline"] = {"value": args.cpu_windows * S / dt, "unit": UNIT, "cores": cores, "kind": "reference",
+                                    "sample": f"{args.cpu_windows} windows x {S} samples ({dt:.1f} s), unmodified reference get_prediction (oracle/_ref), torch CPU fp32"}
+        else:
+            cpu_reference_time(spec, ae_cpu, diff_cpu, 1, S)
+            v, dt = cpu_reference_time(spec, ae_cpu, diff_cpu, args.cpu_windows, S)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{args.cpu_windows} windows x {S} samples ({dt:.1f} s), oracle port of the reference algorithm, torch CPU fp32"}
     print(json.dumps(line))
 
 

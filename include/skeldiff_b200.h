@@ -195,6 +195,9 @@ int  sd_gru_create(int num_nodes, const int32_t* node_types_host, int n_types, i
 /* Optional, only when every gx_i == I: gate-interleaved copies that enable the fused FFMA2 step kernel
  * (h @ W_hh^T + gates in one launch).  Row c' = 96*blk + 32*g + u of the permuted tensors holds original row
  * g*H + 32*blk + u (g = gate r/z/n); w_hh_perm_dev is additionally K-major: [n_types, H, 3H].  bias_*_perm_dev: [N, 3H] = bias[type(n)] in the same order. */
+/* Three bf16 planes of W_hh ([3][n_types][3H][H], w = p0 + p1 + p2 exactly) for the tcgen05 recurrent product
+ * h W_hh^T (recurrent.py:339) of the bf16x3 / bf16 precisions.  Optional: without it the FFMA kernels are used. */
+int  sd_gru_set_bf16x3(sd_gru* g, const uint16_t* w_hh_planes_dev);
 int  sd_gru_set_fused(sd_gru* g, const float* w_ih_perm_dev, const float* w_hh_perm_dev,
                       const float* bias_ih_perm_dev, const float* bias_hh_perm_dev);
 void sd_gru_destroy(sd_gru* g);

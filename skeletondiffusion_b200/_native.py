@@ -70,6 +70,7 @@ SIGNATURES = {
     "sd_motion_metrics": (_I, [_P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P]),
     "sd_gru_create": (_I, [_I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, C.POINTER(_P)]),
     "sd_gru_set_fused": (_I, [_P, _P, _P, _P, _P]),
+    "sd_gru_set_bf16x3": (_I, [_P, _P]),
     "sd_gru_destroy": (None, [_P]),
     "sd_encode_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I]),
     "sd_encode": (_I, [_P, _P, _I, _P, _P, _I, _I, _I, _P, _I, _P, _I, _P]),

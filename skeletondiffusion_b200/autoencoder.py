@@ -104,8 +104,9 @@ class Encoder(nn.Module):
         self.initial_hidden1 = StaticGraphLinear(input_size, hidden_size, num_nodes=num_nodes, node_types=node_types, bias=True, learn_influence=True)
         self.dropout = nn.Dropout(dropout)
 
-    def encode(self, x: torch.Tensor, final_act: int) -> torch.Tensor:
-        """[W, T, N, F] -> [W, N, latent]; final_act is applied on top of fc (ACT_* code)."""
+    def encode(self, x: torch.Tensor, final_act: int, precision: str = "fp32") -> torch.Tensor:
+        """[W, T, N, F] -> [W, N, latent]; final_act is applied on top of fc (ACT_* code).  precision 'bf16x3' / 'bf16' runs
+        the recurrent products on the tcgen05 3-plane kernel (fp32-grade), 'fp32' on the FFMA kernels."""
         nv.require_cuda(x, "observation")
         x = x.float().contiguous()
         W, T, N, Fdim = x.shape
@@ -118,7 +119,7 @@ class Encoder(nn.Module):
         ws = Workspace.get(x.device, lib.sd_encode_workspace_bytes(W, T, N, H, len(plans)), "encode")
         z = torch.empty(W, N, fc.out_features, device=x.device, dtype=torch.float32)
         nv.check(lib.sd_encode(ih.handle, handles, len(plans), fc.handle, x.data_ptr(), W, T, Fdim, z.data_ptr(), final_act,
-                               ws.data_ptr(), nv.PREC_FP32, nv.stream_ptr(x.device)), "sd_encode")
+                               ws.data_ptr(), nv.PRECISIONS[precision], nv.stream_ptr(x.device)), "sd_encode")
         return z
 
     def forward(self, x: torch.Tensor, state=None):
@@ -191,17 +192,18 @@ class AutoEncoder(nn.Module):
         assert z_activation in ["tanh", "identity"], f"z_activation must be either 'tanh' or 'identity', but got {z_activation}"
         self._z_act = z_activation
         self.z_activation = nn.Tanh() if z_activation == "tanh" else nn.Identity()
+        self.precision = "fp32"          # 'bf16x3': recurrent products on the tensor cores (fp32-grade); see get_prediction
 
     def forward(self, x):
         h, _ = self.encoder(x)
         return h
 
-    def get_past_embedding(self, past, state=None):
+    def get_past_embedding(self, past, state=None, precision: str = None):
         """tanh(tanh(fc(h_T))) in one pass: the second activation is fused into the fc epilogue (autoencoder.py:51-55)."""
         enc_tanh, z_tanh = self.encoder.encoder_act == "tanh", self._z_act == "tanh"
         act = nv.ACT_TANH_TANH if (enc_tanh and z_tanh) else (nv.ACT_TANH if (enc_tanh or z_tanh) else nv.ACT_NONE)
         with torch.no_grad():
-            return self.encoder.encode(past, act)
+            return self.encoder.encode(past, act, precision=precision or self.precision)
 
     def get_embedding(self, future, state=None):
         return self.forward(future)
@@ -209,8 +211,8 @@ class AutoEncoder(nn.Module):
     def get_train_embeddings(self, y, past, state=None):
         return self.get_past_embedding(past, state=state), self.get_embedding(y, state=state)
 
-    def decode(self, x: torch.Tensor, h: torch.Tensor, z: torch.Tensor = None, ph=1, state=None, precision: str = "fp32"):
-        out, _ = self.decoder(x=x[:, -2:], h=h, z=z, ph=ph, state=state, precision=precision)     # autoencoder.py:66-73
+    def decode(self, x: torch.Tensor, h: torch.Tensor, z: torch.Tensor = None, ph=1, state=None, precision: str = None):
+        out, _ = self.decoder(x=x[:, -2:], h=h, z=z, ph=ph, state=state, precision=precision or self.precision)     # autoencoder.py:66-73
         return out
 
     def autoencode(self, y, past, ph=1, state=None):

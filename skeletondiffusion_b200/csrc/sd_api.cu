@@ -27,6 +27,15 @@ int check_cuda(cudaError_t e, const char* what) {
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    int& c = cached[dev & 63];
+    if (c == 0) { int v = 148; cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); c = v; }
+    return c;
+}
+
 static inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
 struct Arena {   // carves a caller-owned workspace
@@ -159,6 +168,14 @@ static bool tc3_views_ok(const GlinCall& c) {
            ok(c.epi.residual.ptr, c.epi.residual.sb, c.epi.residual.sn) && c.out.rep == 1;
 }
 
+// out = epilogue(G^ @ (rs * Y)) for a layer with a dense graph influence: the per-sample bulk-copy kernel (sd_mix.cu) where the
+// shape is instantiated, the generic kernel otherwise
+static int mix_epilogue(const sd_glin* L, const float* y, const float* row_scale, const Epilogue& epi, const ViewW& out, int B, cudaStream_t st) {
+    Epilogue e = epi; e.OUT = L->OUT;
+    if (L->G_host && sample_mix_supported(L->N, L->OUT, y, e, out)) return sample_mix_fp32(L->G_host, L->N, L->OUT, y, row_scale, e, out, B, st);
+    return node_mix_fp32(L->G, L->N, L->OUT, y, (long long)L->N * L->OUT, row_scale, e, out, B, st);
+}
+
 static int run_glin(const sd_glin* L, GlinCall c, int precision, cudaStream_t st) {
     if (!L) { set_error("graph-linear layer not set"); return SD_ERR_INVALID; }
     if (c.epi.bias_node == nullptr) c.epi.bias_node = L->bias_node;
@@ -169,13 +186,22 @@ static int run_glin(const sd_glin* L, GlinCall c, int precision, cudaStream_t st
         if (L->planes == 3 && !c.epi.ss_row_idx && glin_tc3_supported(c.a0.width, K1, L->OUT) && tc3_views_ok(c)) {
             if (L->G == nullptr) return glin_tc3_launch(L, c, c.out, true, st);
             if (!c.scratch) { set_error("glin: scratch required for non-identity G"); return SD_ERR_INVALID; }
-            int rc = glin_tc3_launch(L, c, contiguous_view_w(c.scratch, L->N, L->OUT), false, st);
+            // raw products on the tensor cores (no row scale: it belongs to the INPUT node of the mix), then the per-sample mix
+            GlinCall raw = c; raw.row_scale = nullptr;
+            int rc = glin_tc3_launch(L, raw, contiguous_view_w(c.scratch, L->N, L->OUT), false, st);
             if (rc) return rc;
-            return node_mix_fp32(L->G, L->N, L->OUT, c.scratch, (long long)L->N * L->OUT, nullptr, c.epi, c.out, c.B, st);
+            return mix_epilogue(L, c.scratch, c.row_scale, c.epi, c.out, c.B, st);
         }
-        return glin_forward_fp32(L->W, L->Wt, L->K, L->OUT, L->types, L->N, L->G, c, st);
+        return run_glin(L, c, SD_PREC_FP32, st);
     }
     if (precision != SD_PREC_FP32) return glin_forward_tc(L, c, precision, st);
+    if (L->G != nullptr && L->G_host && c.scratch && sample_mix_supported(L->N, L->OUT, c.scratch, c.epi, c.out)) {
+        // exact-fp32 products (FFMA kernels) written raw, then the per-sample mix
+        GlinCall raw = c; raw.row_scale = nullptr; raw.epi = no_epilogue(L->OUT); raw.out = contiguous_view_w(c.scratch, L->N, L->OUT);
+        int rc = glin_forward_fp32(L->W, L->Wt, L->K, L->OUT, L->types, L->N, nullptr, raw, st);
+        if (rc) return rc;
+        return mix_epilogue(L, c.scratch, c.row_scale, c.epi, c.out, c.B, st);
+    }
     return glin_forward_fp32(L->W, L->Wt, L->K, L->OUT, L->types, L->N, L->G, c, st);
 }
 
@@ -212,6 +238,13 @@ int sd_glin_create(int num_nodes, const int32_t* node_types_host, int n_types, i
         L->types.t[n] = (unsigned char)t;
     }
     L->W = weight_dev; L->Wt = nullptr; L->bias_node = bias_node_dev; L->G = g_dev; L->W_bf16 = nullptr; L->planes = 0;
+    L->G_host = nullptr;
+    if (g_dev) {   // host copy: the per-sample mix kernels take G^ by value (constant bank)
+        L->G_host = new (std::nothrow) float[(size_t)num_nodes * num_nodes];
+        if (!L->G_host || cudaMemcpy(L->G_host, g_dev, sizeof(float) * num_nodes * num_nodes, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            delete[] L->G_host; delete L; set_error("sd_glin_create: cannot read the graph-influence matrix"); return SD_ERR_CUDA;
+        }
+    }
     *out = L;
     return SD_OK;
 }
@@ -228,7 +261,7 @@ int sd_glin_set_kmajor(sd_glin* L, const float* weight_kmajor_dev) {
     return SD_OK;
 }
 
-void sd_glin_destroy(sd_glin* L) { delete L; }
+void sd_glin_destroy(sd_glin* L) { if (L) delete[] L->G_host; delete L; }
 
 int sd_glin_forward(const sd_glin* L, const sd_glin_args* a, void* stream) {
     if (!L || !a) { set_error("sd_glin_forward: null argument"); return SD_ERR_INVALID; }
@@ -388,10 +421,21 @@ int sd_denoiser_forward(const sd_denoiser* d, const sd_view* x, const sd_view* x
             // Residual(PreNorm(Attention))  (attention.py:16-17, 44-46, 122-136)
             rc = row_inv_norm_fp32(xb, inv, (long long)rows, C, st);
             if (rc) return rc;
-            rc = call(d->slot[s0 + 2], contiguous_view(xb, N, C), null_view(), inv, -1, SD_ACT_NONE, nullptr, qkv, 3 * hd);
-            if (rc) return rc;
-            rc = node_attention_fp32(qkv, att, B, N, d->heads, d->dim_head, st);
-            if (rc) return rc;
+            const sd_glin* Lq = d->slot[s0 + 2];
+            if (Lq && Lq->G != nullptr && Lq->G_host && !Lq->bias_node && node_attention_mix_supported(N, d->heads, d->dim_head, qkv, att)) {
+                // dense graph influence on to_qkv: the GEMM writes the RAW products and the attention kernel mixes the nodes
+                // (and applies the RMSNorm row factors) in shared memory: no [B, N, 768] mix pass through HBM
+                sd_glin Lraw = *Lq; Lraw.G = nullptr; Lraw.G_host = nullptr;
+                rc = call(&Lraw, contiguous_view(xb, N, C), null_view(), nullptr, -1, SD_ACT_NONE, nullptr, qkv, 3 * hd);
+                if (rc) return rc;
+                rc = node_attention_mix_fp32(Lq->G_host, inv, qkv, att, B, N, d->heads, d->dim_head, st);
+                if (rc) return rc;
+            } else {
+                rc = call(Lq, contiguous_view(xb, N, C), null_view(), inv, -1, SD_ACT_NONE, nullptr, qkv, 3 * hd);
+                if (rc) return rc;
+                rc = node_attention_fp32(qkv, att, B, N, d->heads, d->dim_head, st);
+                if (rc) return rc;
+            }
             rc = call(d->slot[s0 + 3], contiguous_view(att, N, hd), null_view(), nullptr, -1, SD_ACT_NONE, xb, xb, C);
             if (rc) return rc;
         }
@@ -529,7 +573,21 @@ int sd_gru_create(int num_nodes, const int32_t* node_types_host, int n_types, in
     }
     g->W_ih = w_ih_dev; g->W_hh = w_hh_dev; g->bias_ih_seq = bias_ih_seq_dev; g->bias_hh_seq = bias_hh_seq_dev; g->gx_seq = gx_seq_dev;
     g->W_ih_perm = g->W_hh_perm = g->bias_ih_perm = g->bias_hh_perm = nullptr;
+    g->W_hh_planes = nullptr; g->gx_host = nullptr;
+    if (gx_seq_dev) {   // host copy: the per-sample gate kernel takes gx_i by value (constant bank)
+        const size_t n = (size_t)steps * num_nodes * num_nodes;
+        g->gx_host = new (std::nothrow) float[n];
+        if (!g->gx_host || cudaMemcpy(g->gx_host, gx_seq_dev, n * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) {
+            delete[] g->gx_host; delete g; set_error("sd_gru_create: cannot read the graph-influence sequence"); return SD_ERR_CUDA;
+        }
+    }
     *out = g;
+    return SD_OK;
+}
+
+int sd_gru_set_bf16x3(sd_gru* g, const uint16_t* w_hh_planes_dev) {
+    if (!g || !w_hh_planes_dev) { set_error("sd_gru_set_bf16x3: null argument"); return SD_ERR_INVALID; }
+    g->W_hh_planes = w_hh_planes_dev;
     return SD_OK;
 }
 
@@ -542,13 +600,32 @@ int sd_gru_set_fused(sd_gru* g, const float* w_ih_perm_dev, const float* w_hh_pe
     return SD_OK;
 }
 
-void sd_gru_destroy(sd_gru* g) { delete g; }
+void sd_gru_destroy(sd_gru* g) { if (g) delete[] g->gx_host; delete g; }
+
+// raw recurrent product hr = h @ W_hh^T: tcgen05 3-plane kernel (fp32-grade) when the planes are set and the precision allows it,
+// the exact FFMA kernel otherwise
+static int gru_recurrent_product(const sd_gru* g, const View& h, float* hr, int B, int precision, cudaStream_t st);
 
 // raw grouped product out = a @ W^T (no bias, no mix)
 static int gru_product(const float* W, int K, int OUT, const NodeTypes& types, int N, View a0, View a1, ViewW out, int B, cudaStream_t st) {
     GlinCall c;
     c.a0 = a0; c.a1 = a1; c.row_scale = nullptr; c.epi = no_epilogue(OUT); c.out = out; c.scratch = nullptr; c.B = B;
     return glin_forward_fp32(W, nullptr, K, OUT, types, N, nullptr, c, st);
+}
+
+static int gru_recurrent_product(const sd_gru* g, const View& h, float* hr, int B, int precision, cudaStream_t st) {
+    const int N = g->N, H = g->H;
+    if (precision != SD_PREC_FP32 && g->W_hh_planes && glin_tc3_supported(H, 0, 3 * H) &&
+        (reinterpret_cast<uintptr_t>(h.ptr) & 15u) == 0 && h.sb % 4 == 0 && h.sn % 4 == 0) {
+        sd_glin rec;                                   // W_hh viewed as a graph-linear H -> 3H without bias or mix
+        rec.N = N; rec.n_types = g->n_types; rec.K = H; rec.OUT = 3 * H; rec.types = g->types; rec.W = g->W_hh; rec.Wt = nullptr;
+        rec.bias_node = nullptr; rec.G = nullptr; rec.W_bf16 = g->W_hh_planes; rec.planes = 3; rec.G_host = nullptr;
+        GlinCall c;
+        c.a0 = h; c.a1 = null_view(); c.row_scale = nullptr; c.epi = no_epilogue(3 * H); c.scratch = nullptr; c.B = B;
+        c.out = contiguous_view_w(hr, N, 3 * H);
+        return glin_tc3_launch(&rec, c, c.out, false, st);
+    }
+    return gru_product(g->W_hh, H, 3 * H, g->types, N, h, null_view(), contiguous_view_w(hr, N, 3 * H), B, st);
 }
 
 size_t sd_encode_workspace_bytes(int windows, int obs_len, int num_nodes, int hidden, int layers) {
@@ -561,7 +638,6 @@ size_t sd_encode_workspace_bytes(int windows, int obs_len, int num_nodes, int hi
 
 int sd_encode(const sd_glin* initial_hidden, sd_gru* const* layers_host, int n_layers, const sd_glin* fc, const float* obs_dev,
               int windows, int obs_len, int feat, float* z_dev, int final_act, void* workspace_dev, int precision, void* stream) {
-    (void)precision;   // the encoder runs once per window (1/num_samples of the work): fp32 path only
     if (windows == 0) return SD_OK;
     if (!initial_hidden || !layers_host || n_layers <= 0 || !fc || !obs_dev || !z_dev || !workspace_dev) { set_error("sd_encode: null argument"); return SD_ERR_INVALID; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -592,13 +668,28 @@ int sd_encode(const sd_glin* initial_hidden, sd_gru* const* layers_host, int n_l
         if (!g || g->IN != in_w || g->H != H || g->steps < T) { set_error("sd_encode: GRU layer %d shape/steps mismatch", l); return SD_ERR_INVALID; }
         // x-side products of all frames at once: rows (w, t) -> [W*T, N, 3H]
         View a; a.ptr = seq_in; a.sb = (long long)N * in_w; a.sn = in_w; a.rep = 1; a.width = in_w;
-        const bool fused_cell = g->W_hh_perm != nullptr;
+        View xr0; xr0.ptr = xr_all; xr0.sb = (long long)T * N * 3 * H; xr0.sn = 3 * H; xr0.rep = 1; xr0.width = 3 * H;
+        ViewW ho0; ho0.ptr = seq_out; ho0.sb = (long long)T * N * H; ho0.sn = H; ho0.rep = 1; ho0.width = H;
+        // per-sample gate kernel (any graph influence) for dense gx, and for every cell on the tensor-core precisions
+        const bool sample_cell = (g->gx_seq ? g->gx_host != nullptr : precision != SD_PREC_FP32) &&
+                                 gru_sample_supported(N, H, hr, xr0, contiguous_view(h0, N, H), ho0);
+        const bool fused_cell = !sample_cell && g->W_hh_perm != nullptr;
         rc = gru_product(fused_cell ? g->W_ih_perm : g->W_ih, in_w, 3 * H, g->types, N, a, null_view(), contiguous_view_w(xr_all, N, 3 * H), W * T, st);
         if (rc) return rc;
         for (int t = 0; t < T; ++t) {
             View h_in;
             if (t == 0) h_in = contiguous_view(h0, N, H);
             else { h_in.ptr = seq_out + (size_t)(t - 1) * N * H; h_in.sb = (long long)T * N * H; h_in.sn = H; h_in.rep = 1; h_in.width = H; }
+            if (sample_cell) {
+                rc = gru_recurrent_product(g, h_in, hr, W, precision, st);
+                if (rc) return rc;
+                View xr = xr0; xr.ptr = xr_all + (size_t)t * N * 3 * H;
+                ViewW h_out = ho0; h_out.ptr = seq_out + (size_t)t * N * H;
+                rc = gru_sample_fp32(g->gx_host ? g->gx_host + (size_t)t * N * N : nullptr, N, H, hr, xr, g->bias_ih_seq + (size_t)t * N * 3 * H,
+                                     g->bias_hh_seq + (size_t)t * N * 3 * H, h_in, h_out, W, st);
+                if (rc) return rc;
+                continue;
+            }
             if (fused_cell) {   // identity graph influence: h @ W_hh^T and the gates in one FFMA2 kernel, written straight into seq[:, t]
                 View xr; xr.ptr = xr_all + (size_t)t * N * 3 * H; xr.sb = (long long)T * N * 3 * H; xr.sn = 3 * H; xr.rep = 1; xr.width = 3 * H;
                 ViewW h_out; h_out.ptr = seq_out + (size_t)t * N * H; h_out.sb = (long long)T * N * H; h_out.sn = H; h_out.rep = 1; h_out.width = H;
@@ -667,6 +758,32 @@ int sd_decode(const sd_glin* initial_hidden, const sd_gru* cell, const sd_glin* 
         c.out = contiguous_view_w(h, N, H); c.scratch = scratch; c.B = B;
         rc = run_glin(initial_hidden, c, SD_PREC_FP32, st);
         if (rc) return rc;
+    }
+    {
+        // Per step: raw recurrent product (tcgen05 3-plane kernel, or FFMA in the exact-fp32 mode), then the per-sample kernel that
+        // mixes the nodes with gx_i and applies the gates (sd_mix.cu), then the output head with fc's own graph influence.
+        // Used for every dense gx / fc.G, and on the tensor-core precisions also for the identity (faster than the FFMA2 step).
+        const View hv = contiguous_view(h, N, H);
+        const ViewW hw = contiguous_view_w(h, N, H);
+        const bool dense = cell->gx_seq != nullptr || fc->G != nullptr;
+        const bool ok = (cell->gx_seq == nullptr || cell->gx_host) && (fc->G == nullptr || fc->G_host) && gru_head_supported(N, H, feat) &&
+                        gru_sample_supported(N, H, hr, contiguous_view(xr_raw, N, 3 * H), hv, hw);
+        if (ok && (dense || precision != SD_PREC_FP32)) {
+            rc = gru_product(cell->W_ih, cell->IN, 3 * H, cell->types, N, make_view(*x_last), lat, contiguous_view_w(xr_raw, N, 3 * H), B, st);
+            if (rc) return rc;
+            for (int i = 0; i < ph; ++i) {
+                rc = gru_recurrent_product(cell, hv, hr, B, precision, st);
+                if (rc) return rc;
+                // in place: a (sample, 32 units) task reads exactly the h elements it overwrites
+                rc = gru_sample_fp32(cell->gx_host ? cell->gx_host + (size_t)i * N * N : nullptr, N, H, hr, contiguous_view(xr_raw, N, 3 * H),
+                                     cell->bias_ih_seq + (size_t)i * N * 3 * H, cell->bias_hh_seq + (size_t)i * N * 3 * H, hv, hw, B, st);
+                if (rc) return rc;
+                ViewW o; o.ptr = out_dev + (size_t)i * N * feat; o.sb = (long long)ph * N * feat; o.sn = feat; o.rep = 1; o.width = feat;
+                rc = gru_head_fp32(fc->G_host, fc->W, fc->bias_node, fc->types, N, H, feat, hv, o, SD_ACT_TANH, B, st);
+                if (rc) return rc;
+            }
+            return SD_OK;
+        }
     }
     if (cell->W_hh_perm && fc->G == nullptr && feat <= 4) {
         // identity graph influence: one fused FFMA2 kernel per step (h @ W_hh^T + gates) and one tiny output head.

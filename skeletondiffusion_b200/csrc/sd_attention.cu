@@ -11,6 +11,7 @@
 // qkv / out are fp32 (parity path) or bf16 (tensor-core path); the math is fp32 in both.
 #include "sd_internal.h"
 #include "sd_tc.cuh"
+#include "sd_mixmat.cuh"
 #include <math.h>
 #include <stdlib.h>
 
@@ -147,11 +148,8 @@ template <typename T, int DH, int NMAX, int NEXACT>
 static int launch_attention(const T* qkv, T* out, int B, int N, int H, cudaStream_t st) {
     const size_t smem = (size_t)ATT_WARPS * 3 * NMAX * (DH + 4) * sizeof(float);
     auto kern = node_attention_kernel<T, DH, NMAX, NEXACT>;
-    static bool configured = false;
-    if (!configured && smem > 48 * 1024) {
-        SD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    static unsigned long long configured = 0;      // bit d: attribute set on device d (it is per device)
+    if (smem > 48 * 1024) if (int rc_attr = opt_in_smem(kern, (size_t)(smem), configured)) return rc_attr;
     const long long tasks = (long long)B * H;
     long long blocks = (tasks + ATT_WARPS - 1) / ATT_WARPS;
     const long long cap = 148LL * 8;                 // persistent-style grid: a few CTAs per SM, tasks grid-strided
@@ -211,9 +209,14 @@ __device__ __forceinline__ void ab_rotate8(float4 (&x)[8], int n) {
     }
 }
 
-template <int N>
+// MIX: qkv holds the RAW per-node products of to_qkv and the graph-influence mix of that layer (graph_structural.py:41) is done
+// here, in place in shared memory, before the heads read the sample: thread = column (768 columns over 256 threads), the N
+// values of the column scaled by the RMSNorm row factor, N x N FFMAs with G^ in the constant bank (kernel parameter, see
+// sd_mix.cu), written back to the same N slots.  The mixed qkv tensor never exists in HBM.
+template <int N, bool MIX>
 __global__ void __launch_bounds__(AB_THREADS, 1)
-node_attention_bulk_kernel(const float* __restrict__ qkv, float* __restrict__ out, int B) {
+node_attention_bulk_kernel(const float* __restrict__ qkv, float* __restrict__ out, int B, const __grid_constant__ MixMat<N> G,
+                           const float* __restrict__ row_scale) {
     constexpr int ROW = 3 * AB_HEADS * AB_DH;                       // 768 floats per (sample, node) row: q | k | v, each [head][32]
     constexpr int IN_FLOATS = N * ROW, OUT_ROW = AB_HEADS * AB_DH, OUT_FLOATS = N * OUT_ROW;
     constexpr uint32_t IN_BYTES = IN_FLOATS * 4u, OUT_BYTES = OUT_FLOATS * 4u;
@@ -265,6 +268,23 @@ node_attention_bulk_kernel(const float* __restrict__ qkv, float* __restrict__ ou
     for (int k = group; k < my_samples; k += AB_GROUPS) {
         const int stage = k % AB_STAGES;
         tc::mbar_wait(&bars->full[stage], (uint32_t)(k / AB_STAGES) & 1u);
+        if (MIX) {
+            static_assert(AB_GROUPS == 1, "the in-place mix is shared by the eight head warps of one group");
+            float* slab = in_buf + stage * IN_FLOATS;
+            float rs[N];
+            const long long b = (long long)blockIdx.x + (long long)k * gridDim.x;
+#pragma unroll
+            for (int m = 0; m < N; ++m) rs[m] = row_scale ? __ldg(row_scale + b * N + m) : 1.0f;
+            for (int c = threadIdx.x; c < ROW; c += AB_HEADS * 32) {
+                float in[N][1], acc[N][1];
+#pragma unroll
+                for (int m = 0; m < N; ++m) in[m][0] = slab[m * ROW + c] * rs[m];
+                mix_nodes<N, 1>(G, in, acc);
+#pragma unroll
+                for (int n2 = 0; n2 < N; ++n2) slab[n2 * ROW + c] = acc[n2][0];
+            }
+            asm volatile("bar.sync 1, %0;" :: "n"(AB_HEADS * 32) : "memory");      // the eight head warps (not the copy warp)
+        }
         float* blk = in_buf + stage * IN_FLOATS + h * AB_DH;
         if (active) {
             float2 q[16];
@@ -325,21 +345,18 @@ node_attention_bulk_kernel(const float* __restrict__ qkv, float* __restrict__ ou
     }
 }
 
-template <int N>
-static int launch_attention_bulk(const float* qkv, float* out, int B, cudaStream_t st) {
+template <int N, bool MIX>
+static int launch_attention_bulk(const float* qkv, float* out, int B, cudaStream_t st, const float* G_host = nullptr, const float* row_scale = nullptr) {
     constexpr size_t smem = (size_t)(AB_STAGES * N * 3) * AB_HEADS * AB_DH * sizeof(float) + sizeof(AbBarriers) + 128;
     static_assert(smem <= 227 * 1024, "attention ring does not fit shared memory");
-    auto kern = node_attention_bulk_kernel<N>;
-    static bool configured = false;
-    if (!configured) {
-        SD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    MixMat<N> G;
+    G.set(MIX ? G_host : nullptr);
+    auto kern = node_attention_bulk_kernel<N, MIX>;
+    static unsigned long long configured = 0;      // bit d: attribute set on device d (it is per device)
+    if (int rc_attr = opt_in_smem(kern, (size_t)(smem), configured)) return rc_attr;
+    const int sms = sm_count();
     const int grid = B < sms ? B : sms;                             // persistent: one CTA per SM, samples grid-strided
-    kern<<<grid, AB_THREADS, smem, st>>>(qkv, out, B);
+    kern<<<grid, AB_THREADS, smem, st>>>(qkv, out, B, G, row_scale);
     SD_LAUNCH_OK("node_attention_bulk_kernel");
     return SD_OK;
 }
@@ -496,14 +513,9 @@ static int launch_attention_bulk_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* o
     constexpr size_t smem = (size_t)(AB16_STAGES * N * 3) * AB_HEADS * AB_DH * sizeof(__nv_bfloat16) + sizeof(Ab16Barriers) + 128;
     static_assert(smem <= 227 * 1024, "bf16 attention ring does not fit shared memory");
     auto kern = node_attention_bulk_bf16_kernel<N>;
-    static bool configured = false;
-    if (!configured) {
-        SD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    static unsigned long long configured = 0;      // bit d: attribute set on device d (it is per device)
+    if (int rc_attr = opt_in_smem(kern, (size_t)(smem), configured)) return rc_attr;
+    const int sms = sm_count();
     const int grid = B < sms ? B : sms;
     kern<<<grid, AB_THREADS, smem, st>>>(qkv, out, B);
     SD_LAUNCH_OK("node_attention_bulk_bf16_kernel");
@@ -524,9 +536,9 @@ template <> struct BulkAttention<float> {
     static bool run(const float* qkv, float* out, int B, int N, int heads, int dh, cudaStream_t st, int* rc) {
         if (heads != AB_HEADS || dh != AB_DH || attention_legacy_forced()) return false;
         if ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out)) & 15u) return false;
-        if (N == 21) { *rc = launch_attention_bulk<21>(qkv, out, B, st); return true; }    // AMASS
-        if (N == 16) { *rc = launch_attention_bulk<16>(qkv, out, B, st); return true; }    // H36M, README
-        if (N == 17) { *rc = launch_attention_bulk<17>(qkv, out, B, st); return true; }    // FreeMan
+        if (N == 21) { *rc = launch_attention_bulk<21, false>(qkv, out, B, st); return true; }    // AMASS
+        if (N == 16) { *rc = launch_attention_bulk<16, false>(qkv, out, B, st); return true; }    // H36M, README
+        if (N == 17) { *rc = launch_attention_bulk<17, false>(qkv, out, B, st); return true; }    // FreeMan
         return false;
     }
 };
@@ -556,6 +568,19 @@ static int node_attention_any(const T* qkv, T* out, int B, int N, int heads, int
     if (dh == 64 && N <= 32) return launch_attention<T, 64, 32, 0>(qkv, out, B, N, heads, st);
     set_error("node_attention: dim_head %d with %d nodes unsupported (dim_head 32: N<=64; 16/64: N<=32)", dh, N);
     return SD_ERR_UNSUPPORTED;
+}
+
+bool node_attention_mix_supported(int N, int heads, int dh, const float* qkv, const float* out) {
+    if (heads != AB_HEADS || dh != AB_DH || attention_legacy_forced()) return false;
+    if ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out)) & 15u) return false;
+    return N == 21 || N == 16 || N == 17;
+}
+int node_attention_mix_fp32(const float* G_host, const float* row_scale, const float* qkv, float* out, int B, int N, int heads, int dh, cudaStream_t st) {
+    if (B <= 0) return SD_OK;
+    if (!G_host || !node_attention_mix_supported(N, heads, dh, qkv, out)) { set_error("node_attention_mix: unsupported shape"); return SD_ERR_UNSUPPORTED; }
+    if (N == 21) return launch_attention_bulk<21, true>(qkv, out, B, st, G_host, row_scale);
+    if (N == 16) return launch_attention_bulk<16, true>(qkv, out, B, st, G_host, row_scale);
+    return launch_attention_bulk<17, true>(qkv, out, B, st, G_host, row_scale);
 }
 
 int node_attention_fp32(const float* qkv, float* out, int B, int N, int heads, int dh, cudaStream_t st) {

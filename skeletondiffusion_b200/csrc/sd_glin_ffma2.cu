@@ -253,11 +253,8 @@ bool glin_f2_supported(const View& a0, const View& a1, int K, int OUT, const flo
 template <bool GRU>
 static int f2_launch(const F2Params& p, cudaStream_t st) {
     auto kern = glin_gemm_f2_kernel<GRU>;
-    static bool configured = false;
-    if (!configured) {
-        SD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
-        configured = true;
-    }
+    static unsigned long long configured = 0;      // bit d: attribute set on device d (it is per device)
+    if (int rc_attr = opt_in_smem(kern, (size_t)(F2_SMEM), configured)) return rc_attr;
     dim3 grid((p.B + F2_BM - 1) / F2_BM, p.N, p.OUT / F2_BN);
     kern<<<grid, F2_THREADS, F2_SMEM, st>>>(p);
     SD_LAUNCH_OK("glin_gemm_f2_kernel");

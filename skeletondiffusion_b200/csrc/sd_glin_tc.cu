@@ -343,11 +343,8 @@ bool glin_tc_supported(int K0, int K1, int OUT) {
 template <int ACT, bool HAS_RES, bool OUT_FP32>
 static int tc_launch_t(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mw, const TcParams& p, int grid, size_t smem, cudaStream_t st) {
     auto kern = glin_tc_kernel<ACT, HAS_RES, OUT_FP32>;
-    static bool configured = false;
-    if (!configured) {
-        SD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-        configured = true;
-    }
+    static unsigned long long configured = 0;      // bit d: attribute set on device d (it is per device)
+    if (int rc_attr = opt_in_smem(kern, (size_t)((227 * 1024)), configured)) return rc_attr;
     kern<<<grid, TC_THREADS, smem, st>>>(ma0, ma1, mw, p);
     SD_LAUNCH_OK("glin_tc_kernel");
     return SD_OK;
@@ -385,9 +382,7 @@ int glin_tc_launch(const sd_glin* L, const TcCall& c, cudaStream_t st) {
     rc = make_map(&mw, L->W_bf16, (uint64_t)L->K, (uint64_t)L->OUT, (uint64_t)L->n_types, (uint64_t)L->K, (uint64_t)L->OUT * L->K, (uint32_t)p.BN, 1);
     if (rc) return rc;
     const size_t smem = tc_fixed_smem(L->K, p.BN) + (size_t)p.nstage * TC_BM * 128;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = sm_count();
     const long long total = (long long)p.N * p.NT * p.MT;
     const int grid = (int)(total < sms ? total : sms);
     switch (c.act) {

@@ -124,7 +124,6 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
     const long long total = (long long)p.N * p.MT;
     const long long item_lo = total * gang / n_gangs;
     const long long item_hi = total * (gang + 1) / n_gangs;
-    const int KB0 = p.a0.width / T3_BK;
 
     if (warp < 8) {
         // ================================================================ transform producers (256 threads)
@@ -145,21 +144,27 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
         auto fetch = [&](float4 (&v)[8]) {
             if (f_left <= 0) return;
             --f_left;
-            const bool seg0 = f_kb < KB0;
+            // column of the concatenated K axis this thread fetches; the segment is chosen per float4 (segment widths are
+            // multiples of 4, not of 64: cat[x_cond, x] = 96 + 96, the recurrent product has K = 96).  Columns beyond the
+            // last segment are zero planes (the weight planes' out-of-range columns are zero-filled by TMA).
+            const int kcol = f_kb * T3_BK + col4 * 4;
+            const bool seg0 = kcol < p.a0.width;
             const View& seg = seg0 ? p.a0 : p.a1;
-            const float* base = seg.ptr + (long long)f_node * seg.sn + ((seg0 ? f_kb : f_kb - KB0) * T3_BK + col4 * 4);
+            const int scol = seg0 ? kcol : kcol - p.a0.width;
+            const float* base = seg.ptr + (long long)f_node * seg.sn + scol;
+            const int b_end = scol < seg.width ? p.B : 0;
             const int b0 = f_mt * T3_BM + row0;
             if (seg.rep == 1) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int b = b0 + 16 * i;
-                    v[i] = (b < p.B) ? __ldg(reinterpret_cast<const float4*>(base + (long long)b * seg.sb)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[i] = (b < b_end) ? __ldg(reinterpret_cast<const float4*>(base + (long long)b * seg.sb)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int b = b0 + 16 * i;
-                    v[i] = (b < p.B) ? __ldg(reinterpret_cast<const float4*>(base + (long long)(b / seg.rep) * seg.sb)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[i] = (b < b_end) ? __ldg(reinterpret_cast<const float4*>(base + (long long)(b / seg.rep) * seg.sb)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
             if (++f_kb == p.KB) { f_kb = 0; if (++f_mt == p.MT) { f_mt = 0; ++f_node; } }
@@ -403,12 +408,13 @@ typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static size_t t3_misc_smem(int bn) { return 2 * (size_t)bn * 4 + 4 * 32 * 16 * 4 + sizeof(T3Barriers) + 1024; }
-static size_t t3_fixed_smem(int K, int bn) { return (size_t)3 * (K / T3_BK) * bn * 128 + t3_misc_smem(bn); }
+static int t3_kb(int K) { return (K + T3_BK - 1) / T3_BK; }      // the last k-block may be partly filled (zero planes)
+static size_t t3_fixed_smem(int K, int bn) { return (size_t)3 * t3_kb(K) * bn * 128 + t3_misc_smem(bn); }
 // activation-stationary mode: K/64 plane stages + two weight slots of 3 planes; widest n-tile that fits (>= 64 columns)
 static int t3_as_bn(int K, int OUT) {
     const int cands[] = {128, 96, 64};
     for (int bn : cands)
-        if (OUT % bn == 0 && OUT / bn >= 2 && (size_t)(K / T3_BK) * T3_STAGE_BYTES + (size_t)2 * 3 * bn * 128 + t3_misc_smem(bn) <= 227 * 1024) return bn;
+        if (OUT % bn == 0 && OUT / bn >= 2 && (size_t)t3_kb(K) * T3_STAGE_BYTES + (size_t)2 * 3 * bn * 128 + t3_misc_smem(bn) <= 227 * 1024) return bn;
     return 0;
 }
 static int t3_stages(int K, int bn) {
@@ -424,18 +430,16 @@ static int t3_pick_bn(int K, int OUT) {
 }
 
 bool glin_tc3_supported(int K0, int K1, int OUT) {
-    if (K0 <= 0 || K0 % T3_BK || K1 % T3_BK) return false;
+    // segment widths: multiples of 4 (float4 granules); the weight rows (K bf16) must be 16-byte multiples for the TMA map
+    if (K0 <= 0 || K0 % 4 || K1 % 4 || (K0 + K1) % 8) return false;
     return t3_pick_bn(K0 + K1, OUT) != 0;
 }
 
 template <int ACT, bool HAS_RES>
 static int t3_launch_t(const CUtensorMap& mw, const T3Params& p, int grid, size_t smem, cudaStream_t st) {
     auto kern = glin_tc3_kernel<ACT, HAS_RES>;
-    static bool configured = false;
-    if (!configured) {
-        SD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-        configured = true;
-    }
+    static unsigned long long configured = 0;      // bit d: attribute set on device d (it is per device)
+    if (int rc_attr = opt_in_smem(kern, (size_t)((227 * 1024)), configured)) return rc_attr;
     kern<<<grid, T3_THREADS, smem, st>>>(mw, p);
     SD_LAUNCH_OK("glin_tc3_kernel");
     return SD_OK;
@@ -447,7 +451,7 @@ static int t3_launch_one(const sd_glin* L, const GlinCall& c, const ViewW& out, 
     if (!L->W_bf16 || L->planes != 3) { set_error("bf16x3 path: 3-plane weights not set on this layer"); return SD_ERR_INVALID; }
     const int K0 = c.a0.width, K1 = c.a1.ptr ? c.a1.width : 0;
     const int Kuse = K0 + K1;
-    if (k_base < 0 || k_base % T3_BK || k_base + Kuse > L->K || !glin_tc3_supported(K0, K1, L->OUT)) { set_error("bf16x3 path: unsupported shape K=%d+%d (base %d of %d) OUT=%d", K0, K1, k_base, L->K, L->OUT); return SD_ERR_UNSUPPORTED; }
+    if (k_base < 0 || k_base % 8 || k_base + Kuse > L->K || !glin_tc3_supported(K0, K1, L->OUT)) { set_error("bf16x3 path: unsupported shape K=%d+%d (base %d of %d) OUT=%d", K0, K1, k_base, L->K, L->OUT); return SD_ERR_UNSUPPORTED; }
     if (c.epi.ss_row_idx && apply_epilogue) { set_error("bf16x3 path: per-sample time rows are only supported on the FFMA path"); return SD_ERR_UNSUPPORTED; }
     if (c.B <= 0) return SD_OK;
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
@@ -460,7 +464,7 @@ static int t3_launch_one(const sd_glin* L, const GlinCall& c, const ViewW& out, 
     T3Params p;
     p.a0 = c.a0; p.a1 = c.a1; if (!c.a1.ptr) { p.a1 = c.a0; p.a1.width = 0; }
     p.B = c.B; p.N = L->N; p.K = Kuse; p.OUT = L->OUT; p.BN = t3_pick_bn(Kuse, L->OUT); p.NT = L->OUT / p.BN;
-    p.MT = (c.B + T3_BM - 1) / T3_BM; p.KB = Kuse / T3_BK; p.nstage = t3_stages(Kuse, p.BN); p.n_types = L->n_types;
+    p.MT = (c.B + T3_BM - 1) / T3_BM; p.KB = t3_kb(Kuse); p.nstage = t3_stages(Kuse, p.BN); p.n_types = L->n_types;
     p.k_base = k_base;
     if (pre) p.pre = *pre; else { p.pre.ptr = nullptr; p.pre.sb = p.pre.sn = 0; p.pre.rep = 1; p.pre.width = 0; }
     p.a_stationary = 0;
@@ -500,9 +504,7 @@ static int t3_launch_one(const sd_glin* L, const GlinCall& c, const ViewW& out, 
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (weights x3) failed: %d", (int)r); return SD_ERR_CUDA; }
     const size_t smem = (p.a_stationary ? (size_t)2 * 3 * p.BN * 128 + t3_misc_smem(p.BN) : t3_fixed_smem(Kuse, p.BN)) + (size_t)p.nstage * T3_STAGE_BYTES;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = sm_count();
     long long gangs = p.a_stationary ? sms : sms / p.NT;
     if (gangs < 1) gangs = 1;
     if (gangs > (long long)p.N * p.MT) gangs = (long long)p.N * p.MT;
@@ -523,7 +525,7 @@ int glin_tc3_launch(const sd_glin* L, const GlinCall& c, const ViewW& out, bool 
     if (K0 + K1 != L->K) { set_error("bf16x3 path: operand widths %d+%d do not match the layer's K=%d", K0, K1, L->K); return SD_ERR_INVALID; }
     static int split_env = -1;               // SKELDIFF_TC3_KSPLIT=0 disables the K-split (A/B timing)
     if (split_env < 0) { const char* e = getenv("SKELDIFF_TC3_KSPLIT"); split_env = (e && e[0] == '0') ? 0 : 1; }
-    auto stationary_ok = [&](int K) { return K % T3_BK == 0 && K / T3_BK <= T3_MAX_STAGES && t3_as_bn(K, L->OUT) != 0; };
+    auto stationary_ok = [&](int K) { return t3_kb(K) <= T3_MAX_STAGES && t3_as_bn(K, L->OUT) != 0; };
     const bool split = split_env && K1 > 0 && apply_epilogue && c.scratch && c.scratch != out.ptr && !c.row_scale && !c.epi.residual.ptr &&
                        !stationary_ok(L->K) && stationary_ok(K0) && stationary_ok(K1);
     if (!split) return t3_launch_one(L, c, out, apply_epilogue, 0, nullptr, st);

@@ -201,11 +201,8 @@ int gru_step_fused(const float* W_hh_perm_t, int H, const NodeTypes& types, int 
     constexpr int KT = 3;
     const int smem = KT * G2_BM * 128 + G2_STAGES * G2_B_BYTES;
     auto kern = gru_step_fused_kernel<KT>;
-    static bool configured = false;
-    if (!configured) {
-        SD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
-    }
+    static unsigned long long configured = 0;      // bit d: attribute set on device d (it is per device)
+    if (int rc_attr = opt_in_smem(kern, (size_t)(smem), configured)) return rc_attr;
     dim3 grid((B + G2_BM - 1) / G2_BM, N, 1);
     kern<<<grid, G2_THREADS, smem, st>>>(p);
     SD_LAUNCH_OK("gru_step_fused_kernel");

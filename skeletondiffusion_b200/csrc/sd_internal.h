@@ -12,6 +12,7 @@ struct sd_glin {
     const float* G;          // [N][N] or null (identity)
     const uint16_t* W_bf16;  // [planes][n_types][OUT][K] or null
     int planes;
+    float* G_host;           // host copy of G (kernel-parameter constant bank of the per-sample mix kernels) or null
 };
 
 struct sd_gru {
@@ -22,6 +23,8 @@ struct sd_gru {
     const float* bias_ih_seq;  // [steps][N][3H]
     const float* bias_hh_seq;  // [steps][N][3H]
     const float* gx_seq;     // [steps][N][N] or null
+    float* gx_host;          // host copy of gx_seq or null
+    const uint16_t* W_hh_planes;   // [3][n_types][3H][H] bf16 planes of W_hh (tcgen05 recurrent product) or null
     // gate-interleaved copies for the fused FFMA2 GRU step (identity graph influence only); row c' = 96*blk + 32*g + u
     // holds original row g*H + 32*blk + u, so every 96-column GEMM block carries gates r|z|n of 32 units
     const float* W_ih_perm;  // [n_types][3H][IN]
@@ -45,6 +48,19 @@ struct sd_denoiser {
 };
 
 namespace sd {
+
+int sm_count();               // multiprocessors of the current device (cached per device)
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: set it once per (kernel, device)
+template <typename K>
+inline int opt_in_smem(K kern, size_t bytes, unsigned long long& done_mask) {
+    int dev = 0;
+    if (check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return SD_ERR_CUDA;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done_mask & bit) return SD_OK;
+    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes), "cudaFuncSetAttribute")) return SD_ERR_CUDA;
+    done_mask |= bit;
+    return SD_OK;
+}
 
 // generic launcher used by every composite: out = epilogue(G^ @ (A @ W^T))
 struct GlinCall {
@@ -104,6 +120,19 @@ int node_attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int
 // mix of fp32 raw products with bf16 residual / bf16-or-fp32 output
 int node_mix_to_bf16(const float* G, int N, int OUT, const float* y, const Epilogue& epi, const __nv_bfloat16* res,
                      void* out, int out_fp32, int B, cudaStream_t st);
+// per-sample kernels for a general graph influence (sd_mix.cu); G_host / gx: [N][N] on the HOST (passed by value to the kernel)
+bool sample_mix_supported(int N, int OUT, const float* y, const Epilogue& epi, const ViewW& out);
+int sample_mix_fp32(const float* G_host, int N, int OUT, const float* y, const float* row_scale, const Epilogue& epi,
+                    const ViewW& out, int B, cudaStream_t st);
+bool gru_sample_supported(int N, int H, const float* hr, const View& xr, const View& h_prev, const ViewW& h_out);
+int gru_sample_fp32(const float* G_host, int N, int H, const float* hr, const View& xr, const float* bias_x, const float* bias_h,
+                    const View& h_prev, const ViewW& h_out, int B, cudaStream_t st);
+bool gru_head_supported(int N, int H, int F);
+int gru_head_fp32(const float* G_host, const float* Wfc, const float* bias_node, const NodeTypes& types, int N, int H, int F,
+                  const View& h, const ViewW& out, int act, int B, cudaStream_t st);
+// attention with the to_qkv node mix fused in: qkv holds the RAW per-node products, row (b, m) is scaled by row_scale[b*N + m]
+bool node_attention_mix_supported(int N, int heads, int dh, const float* qkv, const float* out);
+int node_attention_mix_fp32(const float* G_host, const float* row_scale, const float* qkv, float* out, int B, int N, int heads, int dh, cudaStream_t st);
 int add_residual_fp32(float* out, const View& res, int B, int N, int OUT, long long out_sb, long long out_sn, cudaStream_t st);
 int gru_gates_fp32(const View& xr, const float* xr_bias, const float* hr, const float* hr_bias,
                    const View& h_in, const ViewW& h_out, int B, int N, int H, cudaStream_t st);

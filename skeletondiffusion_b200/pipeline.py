@@ -56,7 +56,9 @@ def get_diffusion_latent_codes(obs, model, num_samples=50, **kwargs):
     autoencoder, diffusion = model
     bs = obs.shape[0]
     sampler_kwargs = kwargs.get("sampler_kwargs", {})
-    past_embedding = autoencoder.get_past_embedding(obs)
+    # the autoencoder's recurrent products follow the diffusion's precision mode ('bf16x3' is fp32-grade on the tensor cores)
+    prec = getattr(diffusion, "precision", None)
+    past_embedding = autoencoder.get_past_embedding(obs, precision=None if prec in (None, "bf16") else prec)
     if kwargs.get("diffusion_conditioning", True):
         # x_cond has bs rows, the batch bs*num_samples: rows are repeat_interleave'd in place (base.py:246-248)
         latent_pred, _ = diffusion.sample(batch_size=bs * num_samples, x_cond=past_embedding, **sampler_kwargs)
@@ -66,9 +68,11 @@ def get_diffusion_latent_codes(obs, model, num_samples=50, **kwargs):
 
 
 def decode_latent_pred(obs, latent_pred, z_past, model, num_samples=50, pred_length=100, **kwargs):
-    autoencoder, _ = model
+    autoencoder, diffusion = model
     bs, _, j, f = obs.shape
-    pred = autoencoder.decode(obs, latent_pred, z_past, ph=pred_length)       # obs rows shared by the samples of a window
+    prec = getattr(diffusion, "precision", None)
+    pred = autoencoder.decode(obs, latent_pred, z_past, ph=pred_length,        # obs rows shared by the samples of a window
+                              precision=None if prec is None else ("bf16x3" if prec == "bf16" else prec))
     return pred.view(bs, num_samples, pred_length, j, f)
 
 

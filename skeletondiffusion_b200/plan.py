@@ -288,6 +288,13 @@ class GruPlan:
         nv.check(nv.load().sd_gru_create(N, self.types_host, self.w_ih.shape[0], cell.input_size, H, self.w_ih.data_ptr(),
                                          self.w_hh.data_ptr(), self.bias_ih_seq.data_ptr(), self.bias_hh_seq.data_ptr(),
                                          nv.dptr(self.gx_seq), steps, C.byref(self.handle)), "sd_gru_create")
+        # bf16 planes of W_hh for the tcgen05 recurrent product (w = p0 + p1 + p2 exactly), K-major [3, types, 3H, H]
+        p0 = self.w_hh.to(torch.bfloat16)
+        r1 = self.w_hh - p0.float()
+        p1 = r1.to(torch.bfloat16)
+        p2 = (r1 - p1.float()).to(torch.bfloat16)
+        self.w_hh_planes = torch.stack([p0, p1, p2], 0).contiguous()
+        nv.check(nv.load().sd_gru_set_bf16x3(self.handle, self.w_hh_planes.data_ptr()), "sd_gru_set_bf16x3")
         if self.identity and H % 32 == 0:
             # gate-interleaved copies for the fused FFMA2 GRU step: every 96-row block = gates r|z|n of 32 units
             blk = torch.arange(H // 32, device=dev).view(-1, 1, 1)
