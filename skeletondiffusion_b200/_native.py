@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 from pathlib import Path
 from typing import Optional
 
@@ -104,7 +105,22 @@ def last_error() -> str:
     return load().sd_last_error().decode("utf-8", "replace")
 
 
+# Device guard.  The library launches on the CURRENT CUDA device (and sizes its grids from that device's SM count), while the
+# caller's tensors may live on another one (a model on cuda:1 with cuda:0 current).  Every native call in this package has the
+# shape  check(lib.fn(..., stream_ptr(device)), "fn"):  stream_ptr switches to the tensors' device while the arguments are
+# being evaluated, check() switches back once the call has returned (also when it failed).
+_guard = threading.local()
+
+
+def _restore_device() -> None:
+    prev = getattr(_guard, "prev", None)
+    if prev is not None:
+        _guard.prev = None
+        torch.cuda.set_device(prev)
+
+
 def check(rc: int, what: str) -> None:
+    _restore_device()
     if rc != 0:
         raise NativeError(f"{what} failed (status {rc}): {last_error()}")
 
@@ -116,6 +132,14 @@ def require_cuda(t: torch.Tensor, name: str = "tensor") -> None:
 
 
 def stream_ptr(device: torch.device) -> int:
+    """Stream handle of `device`'s current stream; makes `device` the current CUDA device until the matching check()."""
+    device = torch.device(device)
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    cur = torch.cuda.current_device()
+    if idx != cur:
+        if getattr(_guard, "prev", None) is None:
+            _guard.prev = cur
+        torch.cuda.set_device(idx)
     return torch.cuda.current_stream(device).cuda_stream
 
 

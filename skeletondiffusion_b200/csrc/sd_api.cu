@@ -779,7 +779,7 @@ int sd_decode(const sd_glin* initial_hidden, const sd_gru* cell, const sd_glin* 
                                      cell->bias_ih_seq + (size_t)i * N * 3 * H, cell->bias_hh_seq + (size_t)i * N * 3 * H, hv, hw, B, st);
                 if (rc) return rc;
                 ViewW o; o.ptr = out_dev + (size_t)i * N * feat; o.sb = (long long)ph * N * feat; o.sn = feat; o.rep = 1; o.width = feat;
-                rc = gru_head_fp32(fc->G_host, fc->W, fc->bias_node, fc->types, N, H, feat, hv, o, SD_ACT_TANH, B, st);
+                rc = gru_head_fp32(fc->G, fc->W, fc->bias_node, fc->types, fc->n_types, N, H, feat, hv, o, SD_ACT_TANH, B, st);
                 if (rc) return rc;
             }
             return SD_OK;

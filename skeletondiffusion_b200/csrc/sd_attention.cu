@@ -571,6 +571,9 @@ static int node_attention_any(const T* qkv, T* out, int B, int N, int heads, int
 }
 
 bool node_attention_mix_supported(int N, int heads, int dh, const float* qkv, const float* out) {
+    static int off = -1;                         // SKELDIFF_NO_ATT_MIX=1: separate mix pass (A/B timing, bisection)
+    if (off < 0) { const char* e = getenv("SKELDIFF_NO_ATT_MIX"); off = (e && e[0] == '1') ? 1 : 0; }
+    if (off) return false;
     if (heads != AB_HEADS || dh != AB_DH || attention_legacy_forced()) return false;
     if ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out)) & 15u) return false;
     return N == 21 || N == 16 || N == 17;

@@ -128,7 +128,7 @@ bool gru_sample_supported(int N, int H, const float* hr, const View& xr, const V
 int gru_sample_fp32(const float* G_host, int N, int H, const float* hr, const View& xr, const float* bias_x, const float* bias_h,
                     const View& h_prev, const ViewW& h_out, int B, cudaStream_t st);
 bool gru_head_supported(int N, int H, int F);
-int gru_head_fp32(const float* G_host, const float* Wfc, const float* bias_node, const NodeTypes& types, int N, int H, int F,
+int gru_head_fp32(const float* G_dev, const float* Wfc, const float* bias_node, const NodeTypes& types, int n_types, int N, int H, int F,
                   const View& h, const ViewW& out, int act, int B, cudaStream_t st);
 // attention with the to_qkv node mix fused in: qkv holds the RAW per-node products, row (b, m) is scaled by row_scale[b*N + m]
 bool node_attention_mix_supported(int N, int heads, int dh, const float* qkv, const float* out);

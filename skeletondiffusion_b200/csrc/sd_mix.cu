@@ -1,46 +1,33 @@
-// Per-sample node mixing for a general (dense) graph-influence matrix G^.
+// Per-sample kernels for a general (dense) graph-influence matrix G^: the node mix of a StaticGraphLinear with its layer
+// epilogue, and the graph-GRU step after the recurrent product.
 //
 //   out[b,n,:] = epilogue( sum_m G^[n,m] * rs[b,m] * Y[b,m,:] )         (graph_structural.py:30-43, gmm :7-8)
 //
-// The grouped GEMM kernels produce the raw per-node products Y[b,m,:] = x[b,m,:] W[type(m)]^T; the mix couples all
-// nodes of a sample, and a sample's Y rows ([N, OUT] floats, 16 KB for the 192-wide AMASS layers) are ONE contiguous
-// block in HBM.  A persistent CTA therefore streams whole samples through a shared-memory ring with one cp.async.bulk
-// per sample (copy warp), and the compute warps work on (sample, 32-column) tasks: lane = column, the N inputs of the
-// column in registers, N accumulators, N*N FFMAs whose G^ operand comes from the constant bank (the matrix is passed BY
-// VALUE as a __grid_constant__ kernel parameter and the loops are fully unrolled, so every FFMA reads c[0x0][imm]: no
-// load instruction and no register is spent on G^).  The layer epilogue (mixed bias, (scale+1)x+shift, tanh, residual)
-// is applied to the accumulators and the result is written with coalesced 128-byte stores: Y is read once, the output
-// written once.  Bound: HBM (Y + residual + out = 3 x 4 B per element); the FFMA work is N FMAs per element (21 for
-// AMASS: 4.3 GFLOP per 192-wide layer at B = 25 600, 0.06 ms of the FP32 pipe).
+// The grouped GEMM kernels produce the raw per-node products Y[b,m,:] = x[b,m,:] W[type(m)]^T; the mix couples all nodes of
+// a sample.  Work item = (sample, 32 or 64 columns): lane = column, the N inputs of the column in registers, N accumulators,
+// N*N FFMAs whose G^ operand comes from the constant bank (the matrix is passed BY VALUE as a __grid_constant__ kernel
+// parameter, sd_mixmat.cuh).  The epilogue (mixed bias, (scale+1)x+shift, tanh, residual) is applied to the accumulators and
+// the result leaves with coalesced 128-byte stores: Y is read once, the output written once.  Bound: HBM (Y + residual + out
+// = 3 x 4 B per element); the FFMA work is N FMAs per element (21 for AMASS: 4.3 GFLOP per 192-wide layer at B = 25 600).
+//
+// Staging.  Persistent CTAs of 12 warps; every warp owns a PRIVATE ring of shared-memory slots and fetches the [N rows][32 or
+// 64 columns] box of its next items itself with one TMA tensor load per box (lane 0), a few boxes ahead of the one it is
+// working on.  No warp ever waits for another one.  A first version shared one ring between a copy warp and eleven compute
+// warps that each visited only every third phase of a slot: with mbarrier PARITY waits a warp that asks for phase u while the
+// barrier is still in phase u - 1 (two bulk copies completing out of order is enough) passes immediately, reads a half-filled
+// slot and signals `done` for the wrong phase -- run-to-run differences and, rarely, a lost phase (deadlock) at B = 25 600.
+// With private rings every phase of a barrier is waited for by the same warp in order, so the parity is unambiguous.
 #include "sd_internal.h"
 #include "sd_tc.cuh"
 #include "sd_mixmat.cuh"
 #include <stdlib.h>
+#include <cuda.h>
 
 namespace sd {
 
-constexpr int SMIX_WARPS = 11;                 // compute warps; + 1 copy warp = 12 warps (ptxas budgets registers per 4-warp group: 168 per thread)
-constexpr int SMIX_THREADS = (SMIX_WARPS + 1) * 32;
-constexpr int SMIX_MAX_STAGES = 8;
-
-
-struct SmixParams {
-    const float* y;            // [B][N][OUT] raw products, contiguous
-    const float* row_scale;    // [B*N] or null: Y row (b, m) is scaled before the mix (RMSNorm factor of the to_qkv input)
-    const float* bias_node;    // [N][OUT] (already mixed: G^ @ bias[type]) or null
-    const float* ss;           // resolved scale/shift row (scale at [o], shift at [OUT + o]) or null
-    int act;
-    View residual;             // ptr null if none
-    ViewW out;
-    int B, OUT, stages;
-};
-
-struct __align__(8) SmixBarriers { uint64_t full[SMIX_MAX_STAGES], done[SMIX_MAX_STAGES]; };
-
-__device__ __forceinline__ void smix_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(tc::smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(tc::smem_u32(bar)) : "memory");
-}
+constexpr int PSK_WARPS = 12;                  // all compute (ptxas budgets registers per 4-warp group: 168 per thread)
+constexpr int PSK_THREADS = PSK_WARPS * 32;
+constexpr int PSK_SMEM = 200 * 1024;           // ring bytes per CTA (all warps)
 
 // tanh with ~1e-7 absolute error in 7 instructions: (1 - t) / (1 + t), t = exp(-2|x|) (MUFU.EX2 + MUFU.RCP, no branch).
 // Its consumers are linear layers, so the ABSOLUTE error is what propagates; it equals the rounding of a value of magnitude 1.
@@ -48,8 +35,6 @@ __device__ __forceinline__ float smix_tanh(float x) {
     const float t = exp2f(-2.8853900817779268f * fabsf(x));
     return copysignf(__fdividef(1.0f - t, 1.0f + t), x);
 }
-
-// COLS: columns per lane (c and c + 32 of a 64-column task when OUT is a multiple of 64: each constant load feeds two FFMAs)
 // FAST: tanh / sigmoid through MUFU.EX2 + MUFU.RCP (absolute error ~1e-7) instead of libdevice (SKELDIFF_ACCURATE_EPILOGUE=1 selects libdevice)
 template <bool FAST> __device__ __forceinline__ float mix_tanh(float x) { return FAST ? smix_tanh(x) : tanhf(x); }
 template <bool FAST> __device__ __forceinline__ float mix_sigmoid(float v) {
@@ -61,39 +46,80 @@ static bool fast_epilogue() {
     return v == 1;
 }
 
+typedef CUresult (*PskEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// fp32 tensor map of rank 3 or 4 without swizzle (dims / box innermost first, strides in bytes for dims 1..rank-1)
+static int psk_map(CUtensorMap* m, const float* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box) {
+    static PskEncodeFn enc = nullptr;
+    if (!enc) {
+        void* fp = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            set_error("cuTensorMapEncodeTiled unavailable"); return SD_ERR_CUDA;
+        }
+        enc = reinterpret_cast<PskEncodeFn>(fp);
+    }
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("per-sample kernel: cuTensorMapEncodeTiled failed (%d)", (int)r); return SD_ERR_CUDA; }
+    return SD_OK;
+}
+
+// One warp's private ring of `slots` boxes.  issue(j) is called by the whole warp for its j-th box (lane 0 arms the slot's
+// barrier and starts the TMA load; the fence orders the warp's earlier generic-proxy reads of the slot before the copy
+// engine's refill), acquire(j) waits until box j has landed.  Box j lives in slot j % slots, phase (j / slots) & 1.
+struct WarpRing {
+    float* buf; uint64_t* full; int slots, box_floats;
+    __device__ __forceinline__ float* slot_ptr(int j) const { return buf + (size_t)(j % slots) * box_floats; }
+    __device__ __forceinline__ void acquire(int j) const { tc::mbar_wait(&full[j % slots], (uint32_t)(j / slots) & 1u, j); }
+};
+
+struct SmixParams {
+    const float* row_scale;    // [B*N] or null: Y row (b, m) is scaled before the mix (RMSNorm factor of the to_qkv input)
+    const float* bias_node;    // [N][OUT] (already mixed: G^ @ bias[type]) or null
+    const float* ss;           // resolved scale/shift row (scale at [o], shift at [OUT + o]) or null
+    int act;
+    View residual;             // ptr null if none
+    ViewW out;
+    int B, OUT, slots;
+};
+
+// COLS: columns per lane (c and c + 32 of a 64-column item when OUT is a multiple of 64: each constant load feeds two FFMAs)
 template <int N, int ACT, bool HAS_RES, int COLS, bool FAST>
-__global__ void __launch_bounds__(SMIX_THREADS, 1)
-sample_mix_kernel(const __grid_constant__ MixMat<N> G, const SmixParams p) {
-    extern __shared__ __align__(128) float smix_smem[];
-    const int slab = N * p.OUT;                                       // floats per sample
-    float* ring = smix_smem;                                          // [stages][slab]
-    SmixBarriers* bars = reinterpret_cast<SmixBarriers*>(ring + (size_t)p.stages * slab);
+__global__ void __launch_bounds__(PSK_THREADS, 1)
+sample_mix_kernel(const __grid_constant__ MixMat<N> G, const __grid_constant__ CUtensorMap map_y, const SmixParams p) {
+    extern __shared__ __align__(128) float psk_smem[];
+    constexpr int BOX = N * 32 * COLS;                                // floats: [N rows][32 * COLS columns]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int chunks = p.OUT / (32 * COLS);                           // tasks per sample
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < p.stages; ++s) { tc::mbar_init(&bars->full[s], 1); tc::mbar_init(&bars->done[s], (uint32_t)chunks); }
+    WarpRing ring;
+    ring.slots = p.slots; ring.box_floats = BOX;
+    ring.buf = psk_smem + (size_t)warp * p.slots * BOX;
+    ring.full = reinterpret_cast<uint64_t*>(psk_smem + (size_t)PSK_WARPS * p.slots * BOX) + warp * p.slots;
+    if (lane == 0) {
+        if (warp == 0) tc::tma_prefetch_desc(&map_y);
+        for (int s = 0; s < p.slots; ++s) tc::mbar_init(&ring.full[s], 1);
         tc::fence_barrier_init();
     }
-    __syncthreads();
+    __syncwarp();
+    const int chunks = p.OUT / (32 * COLS);                           // items per sample
     const int my_samples = (int)blockIdx.x < p.B ? (p.B - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    const uint32_t slab_bytes = (uint32_t)slab * 4u;
-    if (warp == SMIX_WARPS) {
-        // ------------------------------------------------------------ copy warp: one bulk load per sample
-        if (lane == 0) {
-            for (int k = 0; k < my_samples; ++k) {
-                const int st = k % p.stages;
-                if (k >= p.stages) tc::mbar_wait(&bars->done[st], (uint32_t)(k / p.stages - 1) & 1u);
-                tc::mbar_arrive_expect_tx(&bars->full[st], slab_bytes);
-                smix_bulk_load(ring + (size_t)st * slab, p.y + ((long long)blockIdx.x + (long long)k * gridDim.x) * slab, slab_bytes, &bars->full[st]);
-            }
+    const int items = my_samples * chunks;                            // this CTA's items; warp w takes w, w + WARPS, ...
+    const int n_my = items > warp ? (items - 1 - warp) / PSK_WARPS + 1 : 0;
+    auto issue = [&](int j) {
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (j < n_my && lane == 0) {
+            const int item = warp + j * PSK_WARPS, k = item / chunks, c0 = (item - k * chunks) * (32 * COLS);
+            uint64_t* bar = &ring.full[j % ring.slots];
+            tc::mbar_arrive_expect_tx(bar, (uint32_t)BOX * 4u);
+            tc::tma_load_3d(ring.slot_ptr(j), &map_y, bar, c0, 0, (int)blockIdx.x + k * (int)gridDim.x);
         }
-        return;
-    }
-    // ---------------------------------------------------------------- compute warps: task = (sample k, 32 * COLS columns)
-    const long long tasks = (long long)my_samples * chunks;
-    for (long long task = warp; task < tasks; task += SMIX_WARPS) {
-        const int k = (int)(task / chunks), c = (int)(task % chunks) * (32 * COLS) + lane;
-        const int st = k % p.stages;
+    };
+    for (int j = 0; j < p.slots - 1; ++j) issue(j);
+    for (int j = 0; j < n_my; ++j) {
+        issue(j + p.slots - 1);                                       // refills the slot whose box was read in the previous iteration
+        const int item = warp + j * PSK_WARPS, k = item / chunks, c = (item - k * chunks) * (32 * COLS) + lane;
         const int b = (int)blockIdx.x + k * (int)gridDim.x;
         float res[N][COLS];
         if (HAS_RES) {                                                // the residual row segments are in flight during the mix
@@ -101,30 +127,28 @@ sample_mix_kernel(const __grid_constant__ MixMat<N> G, const SmixParams p) {
 #pragma unroll
             for (int n = 0; n < N; ++n)
 #pragma unroll
-                for (int j = 0; j < COLS; ++j) res[n][j] = __ldg(rb + (long long)n * p.residual.sn + 32 * j);
+                for (int q = 0; q < COLS; ++q) res[n][q] = __ldg(rb + (long long)n * p.residual.sn + 32 * q);
         }
         float mul[COLS], add[COLS];
 #pragma unroll
-        for (int j = 0; j < COLS; ++j) {
-            mul[j] = p.ss ? __ldg(p.ss + c + 32 * j) + 1.0f : 1.0f;
-            add[j] = p.ss ? __ldg(p.ss + p.OUT + c + 32 * j) : 0.0f;
+        for (int q = 0; q < COLS; ++q) {
+            mul[q] = p.ss ? __ldg(p.ss + c + 32 * q) + 1.0f : 1.0f;
+            add[q] = p.ss ? __ldg(p.ss + p.OUT + c + 32 * q) : 0.0f;
         }
-        tc::mbar_wait(&bars->full[st], (uint32_t)(k / p.stages) & 1u);
-        const float* ys = ring + (size_t)st * slab + c;
+        ring.acquire(j);
+        const float* ys = ring.slot_ptr(j) + lane;                    // box [N][32 * COLS]
         float in[N][COLS];
 #pragma unroll
         for (int m = 0; m < N; ++m)
 #pragma unroll
-            for (int j = 0; j < COLS; ++j) in[m][j] = ys[m * p.OUT + 32 * j];
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&bars->done[st]);             // this task's reads of the stage are complete
+            for (int q = 0; q < COLS; ++q) in[m][q] = ys[m * (32 * COLS) + 32 * q];
         if (p.row_scale) {
             const float* rs = p.row_scale + (long long)b * N;
 #pragma unroll
             for (int m = 0; m < N; ++m) {
                 const float r = __ldg(rs + m);
 #pragma unroll
-                for (int j = 0; j < COLS; ++j) in[m][j] *= r;
+                for (int q = 0; q < COLS; ++q) in[m][q] *= r;
             }
         }
         float acc[N][COLS];
@@ -133,61 +157,71 @@ sample_mix_kernel(const __grid_constant__ MixMat<N> G, const SmixParams p) {
 #pragma unroll
         for (int n = 0; n < N; ++n)
 #pragma unroll
-            for (int j = 0; j < COLS; ++j) {
-                float v = acc[n][j];
-                if (p.bias_node) v += __ldg(p.bias_node + n * p.OUT + c + 32 * j);
-                v = fmaf(v, mul[j], add[j]);
+            for (int q = 0; q < COLS; ++q) {
+                float v = acc[n][q];
+                if (p.bias_node) v += __ldg(p.bias_node + n * p.OUT + c + 32 * q);
+                v = fmaf(v, mul[q], add[q]);
                 if (ACT == SD_ACT_TANH) v = mix_tanh<FAST>(v);
                 if (ACT == SD_ACT_TANH_TANH) v = mix_tanh<FAST>(mix_tanh<FAST>(v));
-                if (HAS_RES) v += res[n][j];
-                ob[(long long)n * p.out.sn + 32 * j] = v;
+                if (HAS_RES) v += res[n][q];
+                ob[(long long)n * p.out.sn + 32 * q] = v;
             }
     }
 }
 
 template <int N, int ACT, bool HAS_RES, int COLS, bool FAST>
-static int smix_launch_c(const float* G_host, const SmixParams& p0, cudaStream_t st) {
+static int smix_launch_c(const float* G_host, const float* y, const SmixParams& p0, cudaStream_t st) {
     SmixParams p = p0;
     MixMat<N> G;
     G.set(G_host);
-    const size_t slab_bytes = (size_t)N * p.OUT * 4;
-    int stages = (int)((200 * 1024) / slab_bytes);
-    if (stages > SMIX_MAX_STAGES) stages = SMIX_MAX_STAGES;
-    if (stages < 2) { set_error("sample_mix: a sample's rows (%zu bytes) do not fit a two-stage ring", slab_bytes); return SD_ERR_UNSUPPORTED; }
-    p.stages = stages;
-    const size_t smem = (size_t)stages * slab_bytes + sizeof(SmixBarriers) + 128;
+    const size_t box_bytes = (size_t)N * 32 * COLS * 4;
+    int slots = (int)(PSK_SMEM / (PSK_WARPS * box_bytes));
+    if (slots > 8) slots = 8;
+    if (slots < 2) { set_error("sample_mix: box of %zu bytes does not fit a two-slot ring per warp", box_bytes); return SD_ERR_UNSUPPORTED; }
+    p.slots = slots;
+    CUtensorMap map_y;
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)p.OUT, (cuuint64_t)N, (cuuint64_t)p.B};
+        const cuuint64_t strides[2] = {(cuuint64_t)p.OUT * 4, (cuuint64_t)N * p.OUT * 4};
+        const cuuint32_t box[3] = {(cuuint32_t)(32 * COLS), (cuuint32_t)N, 1};
+        if (int rc = psk_map(&map_y, y, 3, dims, strides, box)) return rc;
+    }
+    const size_t smem = (size_t)PSK_WARPS * slots * (box_bytes + 8) + 128;
     auto kern = sample_mix_kernel<N, ACT, HAS_RES, COLS, FAST>;
     static unsigned long long configured = 0;
     if (int rc = opt_in_smem(kern, 227 * 1024, configured)) return rc;
     const int sms = sm_count();
     const int grid = p.B < sms ? p.B : sms;
-    kern<<<grid, SMIX_THREADS, smem, st>>>(G, p);
+    kern<<<grid, PSK_THREADS, smem, st>>>(G, map_y, p);
     SD_LAUNCH_OK("sample_mix_kernel");
     return SD_OK;
 }
 
 template <int N, int ACT, bool HAS_RES>
-static int smix_launch_t(const float* G_host, const SmixParams& p, cudaStream_t st) {
+static int smix_launch_t(const float* G_host, const float* y, const SmixParams& p, cudaStream_t st) {
     constexpr bool kHasAct = ACT != SD_ACT_NONE;
     const bool fast = kHasAct && fast_epilogue();
-    if (p.OUT % 64 == 0) return fast ? smix_launch_c<N, ACT, HAS_RES, 2, kHasAct>(G_host, p, st) : smix_launch_c<N, ACT, HAS_RES, 2, false>(G_host, p, st);
-    return fast ? smix_launch_c<N, ACT, HAS_RES, 1, kHasAct>(G_host, p, st) : smix_launch_c<N, ACT, HAS_RES, 1, false>(G_host, p, st);
+    if (p.OUT % 64 == 0) return fast ? smix_launch_c<N, ACT, HAS_RES, 2, kHasAct>(G_host, y, p, st) : smix_launch_c<N, ACT, HAS_RES, 2, false>(G_host, y, p, st);
+    return fast ? smix_launch_c<N, ACT, HAS_RES, 1, kHasAct>(G_host, y, p, st) : smix_launch_c<N, ACT, HAS_RES, 1, false>(G_host, y, p, st);
 }
 
 template <int N>
-static int smix_launch_n(const float* G_host, const SmixParams& p, bool has_res, cudaStream_t st) {
+static int smix_launch_n(const float* G_host, const float* y, const SmixParams& p, bool has_res, cudaStream_t st) {
     switch (p.act) {
-    case SD_ACT_NONE: return has_res ? smix_launch_t<N, SD_ACT_NONE, true>(G_host, p, st) : smix_launch_t<N, SD_ACT_NONE, false>(G_host, p, st);
-    case SD_ACT_TANH: return has_res ? smix_launch_t<N, SD_ACT_TANH, true>(G_host, p, st) : smix_launch_t<N, SD_ACT_TANH, false>(G_host, p, st);
-    case SD_ACT_TANH_TANH: return has_res ? smix_launch_t<N, SD_ACT_TANH_TANH, true>(G_host, p, st) : smix_launch_t<N, SD_ACT_TANH_TANH, false>(G_host, p, st);
+    case SD_ACT_NONE: return has_res ? smix_launch_t<N, SD_ACT_NONE, true>(G_host, y, p, st) : smix_launch_t<N, SD_ACT_NONE, false>(G_host, y, p, st);
+    case SD_ACT_TANH: return has_res ? smix_launch_t<N, SD_ACT_TANH, true>(G_host, y, p, st) : smix_launch_t<N, SD_ACT_TANH, false>(G_host, y, p, st);
+    case SD_ACT_TANH_TANH: return has_res ? smix_launch_t<N, SD_ACT_TANH_TANH, true>(G_host, y, p, st) : smix_launch_t<N, SD_ACT_TANH_TANH, false>(G_host, y, p, st);
     }
     set_error("sample_mix: unknown activation %d", p.act);
     return SD_ERR_INVALID;
 }
 
 bool sample_mix_supported(int N, int OUT, const float* y, const Epilogue& epi, const ViewW& out) {
+    static int off = -1;                         // SKELDIFF_NO_SAMPLE_MIX=1: generic node-mix kernel (A/B timing, bisection)
+    if (off < 0) { const char* e = getenv("SKELDIFF_NO_SAMPLE_MIX"); off = (e && e[0] == '1') ? 1 : 0; }
+    if (off) return false;
     if (!(N == 16 || N == 17 || N == 21)) return false;
-    if (OUT % 32 || OUT <= 0 || (size_t)N * OUT * 4 * 2 > 200 * 1024) return false;
+    if (OUT % 32 || OUT <= 0) return false;
     if (reinterpret_cast<uintptr_t>(y) & 15u) return false;
     if (epi.ss_row_idx || out.rep != 1) return false;                 // per-sample time rows: generic kernel
     return true;
@@ -198,17 +232,16 @@ int sample_mix_fp32(const float* G_host, int N, int OUT, const float* y, const f
                     const ViewW& out, int B, cudaStream_t st) {
     if (B <= 0) return SD_OK;
     SmixParams p;
-    p.y = y; p.row_scale = row_scale; p.bias_node = epi.bias_node;
+    p.row_scale = row_scale; p.bias_node = epi.bias_node;
     p.ss = epi.ss ? epi.ss + (long long)epi.ss_row * epi.ss_stride : nullptr;
-    p.act = epi.act; p.residual = epi.residual; p.out = out; p.B = B; p.OUT = OUT; p.stages = 0;
+    p.act = epi.act; p.residual = epi.residual; p.out = out; p.B = B; p.OUT = OUT; p.slots = 0;
     const bool has_res = epi.residual.ptr != nullptr;
-    if (N == 21) return smix_launch_n<21>(G_host, p, has_res, st);
-    if (N == 16) return smix_launch_n<16>(G_host, p, has_res, st);
-    if (N == 17) return smix_launch_n<17>(G_host, p, has_res, st);
+    if (N == 21) return smix_launch_n<21>(G_host, y, p, has_res, st);
+    if (N == 16) return smix_launch_n<16>(G_host, y, p, has_res, st);
+    if (N == 17) return smix_launch_n<17>(G_host, y, p, has_res, st);
     set_error("sample_mix: %d nodes not instantiated", N);
     return SD_ERR_UNSUPPORTED;
 }
-
 
 // =====================================================================================================================
 // Graph-GRU step after the recurrent product, general graph influence gx_i (recurrent.py:333-358):
@@ -216,116 +249,89 @@ int sample_mix_fp32(const float* G_host, int N, int OUT, const float* y, const f
 //     r = sig(xr_r + hr_r), z = sig(xr_z + hr_z), n = tanh(xr_n + r * hr_n), h' = n - n z + z h
 // The raw products x W_ih^T (loop invariant in the decoder, decoder.py:81,93) and h W_hh^T (tcgen05 kernel, one launch per
 // step) arrive as [B, N, 3H] fp32; the mix is linear, so r and z need ONE mix each (of xr + hr) and n needs two: four
-// N x N mixes per hidden unit.  Stage = (sample, 32 hidden units): 6 N row segments of 128 B from the two product tensors
-// and N from h, fetched by the 32 lanes of the copy warp with one cp.async.bulk each; compute warp = one stage, lane = unit.
-// gx_i @ bias is precomputed per step (plan.py).  MIX = false (every gx_i = I) skips the FFMAs: the kernel is then the plain
-// gate kernel with bulk-copy staging.
+// N x N mixes per hidden unit, run as a non-unrolled loop over the phases r, z, hr_n, xr_n.  Item = (sample, 32 hidden
+// units); it consumes seven [N][32] boxes in the order hr_r, xr_r, hr_z, xr_z, hr_n, xr_n, h, each one TMA tensor load into
+// the warp's private ring (see the header), fetched a few boxes ahead.  gx_i @ bias is precomputed per step (plan.py).
+// MIX = false (every gx_i = I) skips the FFMAs: the kernel is then the plain gate kernel.
 // =====================================================================================================================
-constexpr int GRS_WARPS = 11, GRS_THREADS = (GRS_WARPS + 1) * 32, GRS_MAX_STAGES = 12;      // 11 compute warps + 1 copy warp
-
 struct GruSampleParams {
-    const float* hr;           // [B][N][3H] raw h W_hh^T
-    View xr;                   // raw x W_ih^T: row (b, n) = 3H floats
-    View h_prev;               // row (b, n) = H floats
     const float* bias_x;       // [N][3H] = gx_i @ b_ih[type] or null
     const float* bias_h;       // [N][3H]
     ViewW h_out;
-    int B, H, stages;
+    int B, H, slots;
 };
-struct __align__(8) GrsBarriers { uint64_t full[GRS_MAX_STAGES], done[GRS_MAX_STAGES]; };
-
 
 template <int N, bool MIX, bool FAST>
-__global__ void __launch_bounds__(GRS_THREADS, 1)
-gru_sample_kernel(const __grid_constant__ MixMat<N> G, const GruSampleParams p) {
-    extern __shared__ __align__(128) float grs_smem[];
-    constexpr int SEG = 32;                                           // floats per row segment (128 B)
-    constexpr int STAGE_FLOATS = 7 * N * SEG;                         // [hr r|z|n][N][32] [xr r|z|n][N][32] [h][N][32]
-    GrsBarriers* bars = reinterpret_cast<GrsBarriers*>(grs_smem + (size_t)p.stages * STAGE_FLOATS);
+__global__ void __launch_bounds__(PSK_THREADS, 1)
+gru_sample_kernel(const __grid_constant__ MixMat<N> G, const __grid_constant__ CUtensorMap map_hr, const __grid_constant__ CUtensorMap map_xr,
+                  const __grid_constant__ CUtensorMap map_h, const GruSampleParams p) {
+    extern __shared__ __align__(128) float psk_smem[];
+    constexpr int BOX = N * 32, BPI = 7;                              // box [N][32] floats; boxes per item
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int chunks = p.H / SEG;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < p.stages; ++s) { tc::mbar_init(&bars->full[s], 1); tc::mbar_init(&bars->done[s], 1); }
+    WarpRing ring;
+    ring.slots = p.slots; ring.box_floats = BOX;
+    ring.buf = psk_smem + (size_t)warp * p.slots * BOX;
+    ring.full = reinterpret_cast<uint64_t*>(psk_smem + (size_t)PSK_WARPS * p.slots * BOX) + warp * p.slots;
+    if (lane == 0) {
+        if (warp == 0) { tc::tma_prefetch_desc(&map_hr); tc::tma_prefetch_desc(&map_xr); tc::tma_prefetch_desc(&map_h); }
+        for (int s = 0; s < p.slots; ++s) tc::mbar_init(&ring.full[s], 1);
         tc::fence_barrier_init();
     }
-    __syncthreads();
-    // task t = (round r, chunk c, warp w): sample k = r * WARPS + w of this CTA's list, hidden units [32 c, 32 c + 32)
+    __syncwarp();
+    const int chunks = p.H / 32;
     const int my_samples = (int)blockIdx.x < p.B ? (p.B - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    const int rounds = (my_samples + GRS_WARPS - 1) / GRS_WARPS;
-    const long long tasks = (long long)rounds * chunks * GRS_WARPS;
+    const int items = my_samples * chunks;
+    const int n_my = items > warp ? (items - 1 - warp) / PSK_WARPS + 1 : 0;
+    const int n_boxes = n_my * BPI;
     const int H3 = 3 * p.H;
-    if (warp == GRS_WARPS) {
-        // ------------------------------------------------------------ copy warp: 7 N segments per stage, one bulk copy each
-        long long q = 0;                                              // sequence number over the tasks that exist
-        for (long long t = 0; t < tasks; ++t) {
-            const int w = (int)(t % GRS_WARPS), c = (int)((t / GRS_WARPS) % chunks), r = (int)(t / ((long long)GRS_WARPS * chunks));
-            const int k = r * GRS_WARPS + w;
-            if (k >= my_samples) continue;
-            const int st = (int)(q % p.stages);
-            const long long use = q / p.stages;
-            ++q;
-            if (use > 0) tc::mbar_wait(&bars->done[st], (uint32_t)(use - 1) & 1u);
-            if (lane == 0) tc::mbar_arrive_expect_tx(&bars->full[st], (uint32_t)STAGE_FLOATS * 4u);
-            __syncwarp();
-            const long long b = (long long)blockIdx.x + (long long)k * gridDim.x;
-            float* dst = grs_smem + (size_t)st * STAGE_FLOATS;
-            const float* hr_b = p.hr + b * N * H3 + c * SEG;
-            const float* xr_b = p.xr.ptr + (p.xr.rep == 1 ? b : b / p.xr.rep) * p.xr.sb + c * SEG;
-            const float* h_b = p.h_prev.ptr + (p.h_prev.rep == 1 ? b : b / p.h_prev.rep) * p.h_prev.sb + c * SEG;
-            for (int i = lane; i < 7 * N; i += 32) {
-                const int arr = i / (3 * N);                          // 0: hr, 1: xr, 2: h
-                const int rem = i - arr * 3 * N;
-                const int g = rem / N, n = rem - g * N;
-                const float* src = arr == 0 ? hr_b + (long long)n * H3 + g * p.H
-                                 : arr == 1 ? xr_b + (long long)n * p.xr.sn + g * p.H
-                                            : h_b + (long long)n * p.h_prev.sn;
-                smix_bulk_load(dst + i * SEG, src, SEG * 4u, &bars->full[st]);
-            }
+    // box j of this warp: item j / 7, part j % 7 = (hr_r, xr_r, hr_z, xr_z, hr_n, xr_n, h)
+    auto issue = [&](int j) {
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (j < n_boxes && lane == 0) {
+            const int it = j / BPI, part = j - it * BPI;
+            const int item = warp + it * PSK_WARPS, k = item / chunks, c0 = (item - k * chunks) * 32;
+            const int b = (int)blockIdx.x + k * (int)gridDim.x;
+            uint64_t* bar = &ring.full[j % ring.slots];
+            tc::mbar_arrive_expect_tx(bar, (uint32_t)BOX * 4u);
+            if (part == 6) tc::tma_load_3d(ring.slot_ptr(j), &map_h, bar, c0, 0, b);
+            else tc::tma_load_4d(ring.slot_ptr(j), (part & 1) ? &map_xr : &map_hr, bar, c0, part >> 1, 0, b);
         }
-        return;
-    }
-    for (long long t = warp; t < tasks; t += GRS_WARPS) {
-        const int c = (int)((t / GRS_WARPS) % chunks), r = (int)(t / ((long long)GRS_WARPS * chunks));
-        const int k = r * GRS_WARPS + warp;
-        if (k >= my_samples) continue;
-        // sequence number of this task among the tasks that exist (the last round may have fewer than WARPS samples)
-        const int full_rounds = my_samples / GRS_WARPS, tail = my_samples - full_rounds * GRS_WARPS;
-        const long long q = r < full_rounds ? t : (long long)full_rounds * chunks * GRS_WARPS + (long long)c * tail + warp;
-        const int st = (int)(q % p.stages);
-        tc::mbar_wait(&bars->full[st], (uint32_t)(q / p.stages) & 1u);
-        const float* s = grs_smem + (size_t)st * STAGE_FLOATS + lane;
-        const int u = c * SEG + lane;
-        // gate g of node n: hr at s[(g*N + n)*32], xr at s[((3+g)*N + n)*32], h at s[(6*N + n)*32]
-        // the four mixes run one after the other and each reads its inputs from the stage right before it (keeping all five
-        // input sets in registers next to the accumulators spilled 2 KB per thread); the stage is released after the last read
+    };
+    for (int j = 0; j < p.slots - 1; ++j) issue(j);
+    int jb = 0;                                                       // next box to consume
+    for (int it = 0; it < n_my; ++it) {
+        const int item = warp + it * PSK_WARPS, k = item / chunks, u = (item - k * chunks) * 32 + lane;
         const long long b = (long long)blockIdx.x + (long long)k * gridDim.x;
         float* ob = p.h_out.ptr + b * p.h_out.sb + u;
-        auto mix = [&](const float (&in)[N][1], float (&out)[N][1]) {
-            if (MIX) { mix_nodes<N, 1>(G, in, out); return; }
-#pragma unroll
-            for (int n = 0; n < N; ++n) out[n][0] = in[n][0];
-        };
-        // The four mixes run as a NON-unrolled loop over the phases r, z, hr_n, xr_n: unrolled, the compiler keeps the N*N
-        // coefficients of G in registers across the four copies (2 KB of spills per thread); each phase reads its inputs from
-        // the stage right before its mix, and the stage is released after the last read.
         float in[N][1], acc[N][1], rg[N], zg[N], hp[N];
+        // consume one box: refill the slot freed one box earlier, then wait for this one
+        auto take = [&]() -> const float* {
+            issue(jb + p.slots - 1);
+            ring.acquire(jb);
+            return ring.slot_ptr(jb++) + lane;
+        };
 #pragma unroll 1
         for (int ph = 0; ph < 4; ++ph) {
-            const float* sa = s + (ph < 3 ? ph : 5) * N * SEG;        // hr_r, hr_z, hr_n, xr_n
+            // phases 0, 1: hr_g + xr_g (the mix is linear); 2: hr_n; 3: xr_n, then h
+            const float* s0 = take();
 #pragma unroll
-            for (int n = 0; n < N; ++n) in[n][0] = sa[n * SEG];
+            for (int n = 0; n < N; ++n) in[n][0] = s0[n * 32];
             if (ph < 2) {
-                const float* sx = s + (3 + ph) * N * SEG;              // + xr_r, xr_z (the mix is linear)
+                const float* s1 = take();
 #pragma unroll
-                for (int n = 0; n < N; ++n) in[n][0] += sx[n * SEG];
+                for (int n = 0; n < N; ++n) in[n][0] += s1[n * 32];
             }
             if (ph == 3) {
+                const float* s2 = take();
 #pragma unroll
-                for (int n = 0; n < N; ++n) hp[n] = s[(6 * N + n) * SEG];
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&bars->done[st]);     // the stage may be refilled
+                for (int n = 0; n < N; ++n) hp[n] = s2[n * 32];
             }
-            mix(in, acc);
+            if (MIX) mix_nodes<N, 1>(G, in, acc);
+            else {
+#pragma unroll
+                for (int n = 0; n < N; ++n) acc[n][0] = in[n][0];
+            }
             if (ph == 0) {
 #pragma unroll
                 for (int n = 0; n < N; ++n) {
@@ -361,21 +367,35 @@ gru_sample_kernel(const __grid_constant__ MixMat<N> G, const GruSampleParams p) 
 }
 
 template <int N, bool MIX, bool FAST>
-static int grs_launch_t(const float* G_host, const GruSampleParams& p0, cudaStream_t st) {
+static int grs_launch_t(const float* G_host, const float* hr, const View& xr, const View& h_prev, const GruSampleParams& p0, cudaStream_t st) {
     GruSampleParams p = p0;
     MixMat<N> G;
     G.set(MIX ? G_host : nullptr);
-    const size_t stage_bytes = (size_t)7 * N * 32 * 4;
-    int stages = (int)((220 * 1024) / stage_bytes);
-    if (stages > GRS_MAX_STAGES) stages = GRS_MAX_STAGES;
-    p.stages = stages;
-    const size_t smem = stages * stage_bytes + sizeof(GrsBarriers) + 128;
+    CUtensorMap map_hr, map_xr, map_h;
+    {   // gate g of node n of sample b: [b][n][g][u]; a box is [N nodes][32 units] of one gate
+        const cuuint64_t H = (cuuint64_t)p.H, B = (cuuint64_t)p.B;
+        const cuuint64_t d4[4] = {H, 3, (cuuint64_t)N, B};
+        const cuuint32_t b4[4] = {32, 1, (cuuint32_t)N, 1};
+        const cuuint64_t s_hr[3] = {H * 4, 3 * H * 4, (cuuint64_t)N * 3 * H * 4};
+        const cuuint64_t s_xr[3] = {H * 4, (cuuint64_t)xr.sn * 4, (cuuint64_t)xr.sb * 4};
+        const cuuint64_t d3[3] = {H, (cuuint64_t)N, B};
+        const cuuint32_t b3[3] = {32, (cuuint32_t)N, 1};
+        const cuuint64_t s_h[2] = {(cuuint64_t)h_prev.sn * 4, (cuuint64_t)h_prev.sb * 4};
+        if (int rc = psk_map(&map_hr, hr, 4, d4, s_hr, b4)) return rc;
+        if (int rc = psk_map(&map_xr, xr.ptr, 4, d4, s_xr, b4)) return rc;
+        if (int rc = psk_map(&map_h, h_prev.ptr, 3, d3, s_h, b3)) return rc;
+    }
+    const size_t box_bytes = (size_t)N * 32 * 4;
+    int slots = (int)(PSK_SMEM / (PSK_WARPS * box_bytes));
+    if (slots > 7) slots = 7;
+    p.slots = slots;
+    const size_t smem = (size_t)PSK_WARPS * slots * (box_bytes + 8) + 128;
     auto kern = gru_sample_kernel<N, MIX, FAST>;
     static unsigned long long configured = 0;
     if (int rc = opt_in_smem(kern, 227 * 1024, configured)) return rc;
     const int sms = sm_count();
     const int grid = p.B < sms ? p.B : sms;
-    kern<<<grid, GRS_THREADS, smem, st>>>(G, p);
+    kern<<<grid, PSK_THREADS, smem, st>>>(G, map_hr, map_xr, map_h, p);
     SD_LAUNCH_OK("gru_sample_kernel");
     return SD_OK;
 }
@@ -385,7 +405,7 @@ bool gru_sample_supported(int N, int H, const float* hr, const View& xr, const V
     if (H % 32) return false;
     auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
     if (!al(hr) || !al(xr.ptr) || !al(h_prev.ptr) || xr.sb % 4 || xr.sn % 4 || h_prev.sb % 4 || h_prev.sn % 4) return false;
-    return h_out.rep == 1;
+    return h_out.rep == 1 && xr.rep == 1 && h_prev.rep == 1;          // TMA boxes address sample b directly
 }
 
 // h' = GRU gates of one step from the raw products; G_host = gx_i ([N][N], host) or null for the identity
@@ -393,11 +413,11 @@ int gru_sample_fp32(const float* G_host, int N, int H, const float* hr, const Vi
                     const View& h_prev, const ViewW& h_out, int B, cudaStream_t st) {
     if (B <= 0) return SD_OK;
     GruSampleParams p;
-    p.hr = hr; p.xr = xr; p.h_prev = h_prev; p.bias_x = bias_x; p.bias_h = bias_h; p.h_out = h_out; p.B = B; p.H = H; p.stages = 0;
+    p.bias_x = bias_x; p.bias_h = bias_h; p.h_out = h_out; p.B = B; p.H = H; p.slots = 0;
     if ((bias_x == nullptr) != (bias_h == nullptr)) { set_error("gru_sample: both bias tables or none"); return SD_ERR_INVALID; }
     const bool fast = fast_epilogue();
-#define SD_GRS(NN) if (N == NN) return G_host ? (fast ? grs_launch_t<NN, true, true>(G_host, p, st) : grs_launch_t<NN, true, false>(G_host, p, st)) \
-                                              : (fast ? grs_launch_t<NN, false, true>(G_host, p, st) : grs_launch_t<NN, false, false>(G_host, p, st));
+#define SD_GRS(NN) if (N == NN) return G_host ? (fast ? grs_launch_t<NN, true, true>(G_host, hr, xr, h_prev, p, st) : grs_launch_t<NN, true, false>(G_host, hr, xr, h_prev, p, st)) \
+                                              : (fast ? grs_launch_t<NN, false, true>(G_host, hr, xr, h_prev, p, st) : grs_launch_t<NN, false, false>(G_host, hr, xr, h_prev, p, st));
     SD_GRS(21) SD_GRS(16) SD_GRS(17)
 #undef SD_GRS
     set_error("gru_sample: %d nodes not instantiated", N);
@@ -406,45 +426,63 @@ int gru_sample_fp32(const float* G_host, int N, int H, const float* hr, const Vi
 
 // =====================================================================================================================
 // Decoder output head with a general graph influence: y[b,n,:] = act( sum_m G^[n,m] (W_fc[type(m)] h[b,m,:]) + bias_node[n] )
-// (decoder.py:97-98 through graph_structural.py:30-43).  F <= 4 outputs per node.  One warp per sample: lane l < N owns node l
-// for the H-long dot products (h rows read with coalesced float4 loads through shared memory), then the N x N mix.
+// (decoder.py:97-98 through graph_structural.py:30-43).  F <= 3 outputs per node, N F <= 64.  One warp per sample: lane = hidden
+// unit (coalesced 128-byte reads of the h rows, W_fc and G^ in shared memory), the N F partial dot products of the lanes are
+// summed with a butterfly reduce-scatter (62 shuffles for 64 values instead of 5 per value), then the N x N mix.
+// HBM-bound: reads h once (206 MB at B = 25 600), writes 6 MB.
 // =====================================================================================================================
 constexpr int GHD_WARPS = 8;
 
-template <int N>
+template <int N, int F>
 __global__ void __launch_bounds__(GHD_WARPS * 32)
-gru_head_kernel(const __grid_constant__ MixMat<N> G, const float* __restrict__ Wfc, const float* __restrict__ bias_node, const NodeTypes types,
-                int H, int F, const View h, const ViewW out, int act, int B) {
-    extern __shared__ __align__(16) float ghd_smem[];                 // [warps][N][H + 1] rows + [warps][N][4] products
+gru_head_kernel(const float* __restrict__ G, const float* __restrict__ Wfc, const float* __restrict__ bias_node, const NodeTypes types,
+                int H, int n_types, const View h, const ViewW out, int act, int B) {
+    extern __shared__ __align__(16) float ghd_smem[];                 // [n_types * F * H] weights, [N * N] G^, [warps][64] products
+    float* w_s = ghd_smem;
+    float* g_s = w_s + n_types * F * H;
+    float* p_s = g_s + N * N + (threadIdx.x >> 5) * 64;
+    for (int i = threadIdx.x; i < n_types * F * H; i += blockDim.x) w_s[i] = __ldg(Wfc + i);
+    for (int i = threadIdx.x; i < N * N; i += blockDim.x) g_s[i] = G ? __ldg(G + i) : ((i / N == i % N) ? 1.0f : 0.0f);
+    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int LD = H + 1;
-    float* rows = ghd_smem + (size_t)warp * (N * LD + N * 4);
-    float* prod = rows + N * LD;
     for (int b = blockIdx.x * GHD_WARPS + warp; b < B; b += gridDim.x * GHD_WARPS) {
-        const float* hb = h.ptr + (long long)(h.rep == 1 ? b : b / h.rep) * h.sb;
-        __syncwarp();
-        for (int i = lane; i < N * H; i += 32) {
-            const int n = i / H, u = i - n * H;
-            rows[n * LD + u] = __ldg(hb + (long long)n * h.sn + u);
-        }
-        __syncwarp();
-        if (lane < N) {
-            const float* w = Wfc + (long long)types.t[lane] * F * H;
-            float a[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int u = 0; u < H; ++u) {
-                const float hv = rows[lane * LD + u];
+        const float* hb = h.ptr + (long long)(h.rep == 1 ? b : b / h.rep) * h.sb + lane;
+        float c[64];
 #pragma unroll
-                for (int f = 0; f < 4; ++f) if (f < F) a[f] = fmaf(__ldg(w + f * H + u), hv, a[f]);
+        for (int i = 0; i < 64; ++i) c[i] = 0.0f;
+        for (int u0 = 0; u0 < H; u0 += 32) {
+            float hv[N];
+#pragma unroll
+            for (int n = 0; n < N; ++n) hv[n] = (u0 + lane < H) ? __ldg(hb + (long long)n * h.sn + u0) : 0.0f;
+#pragma unroll
+            for (int n = 0; n < N; ++n) {
+                const float* w = w_s + types.t[n] * F * H + u0 + lane;
+#pragma unroll
+                for (int f = 0; f < F; ++f) c[n * F + f] = fmaf(hv[n], (u0 + lane < H) ? w[f * H] : 0.0f, c[n * F + f]);
             }
-#pragma unroll
-            for (int f = 0; f < 4; ++f) prod[lane * 4 + f] = a[f];
         }
+        // butterfly reduce-scatter over the 32 lanes: after the step with mask m a lane keeps the half of its values selected by
+        // its bit m; lane L ends with the complete sums of indices base, base + 1, base = 32 b4 + 16 b3 + 8 b2 + 4 b1 + 2 b0
+#pragma unroll
+        for (int half = 32, mask = 16; half >= 2; half >>= 1, mask >>= 1) {
+            const bool hi = (lane & mask) != 0;
+#pragma unroll
+            for (int i = 0; i < half; ++i) {
+                const float send = hi ? c[i] : c[i + half];
+                const float keep = hi ? c[i + half] : c[i];
+                c[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+            }
+        }
+        const int base = ((lane & 16) ? 32 : 0) + ((lane & 8) ? 16 : 0) + ((lane & 4) ? 8 : 0) + ((lane & 2) ? 4 : 0) + ((lane & 1) ? 2 : 0);
+        __syncwarp();
+        p_s[base] = c[0];
+        p_s[base + 1] = c[1];
         __syncwarp();
         for (int i = lane; i < N * F; i += 32) {
             const int n = i / F, f = i - n * F;
             float v = 0.0f;
-            const float* gcol = reinterpret_cast<const float*>(&G.g4[0][0]);            // g4[m][q] component j = G^[4q + j][m]
-            for (int m = 0; m < N; ++m) v = fmaf(gcol[(m * MixMat<N>::Q + (n >> 2)) * 4 + (n & 3)], prod[m * 4 + f], v);
+#pragma unroll
+            for (int m = 0; m < N; ++m) v = fmaf(g_s[n * N + m], p_s[m * F + f], v);
             if (bias_node) v += __ldg(bias_node + n * F + f);
             if (act == SD_ACT_TANH) v = tanhf(v);
             out.ptr[(long long)b * out.sb + (long long)n * out.sn + f] = v;
@@ -452,31 +490,34 @@ gru_head_kernel(const __grid_constant__ MixMat<N> G, const float* __restrict__ W
     }
 }
 
-template <int N>
-static int ghd_launch(const float* G_host, const float* Wfc, const float* bias_node, const NodeTypes& types, int H, int F,
+template <int N, int F>
+static int ghd_launch(const float* G_dev, const float* Wfc, const float* bias_node, const NodeTypes& types, int n_types, int H,
                       const View& h, const ViewW& out, int act, int B, cudaStream_t st) {
-    MixMat<N> G;
-    G.set(G_host);
-    const size_t smem = (size_t)GHD_WARPS * (N * (H + 1) + N * 4) * sizeof(float);
-    auto kern = gru_head_kernel<N>;
+    static_assert(N * F <= 64, "the reduce-scatter holds 64 values");
+    const size_t smem = ((size_t)n_types * F * H + N * N + GHD_WARPS * 64) * sizeof(float);
+    auto kern = gru_head_kernel<N, F>;
     static unsigned long long configured = 0;
-    if (int rc = opt_in_smem(kern, 160 * 1024, configured)) return rc;
+    if (smem > 48 * 1024) if (int rc = opt_in_smem(kern, smem, configured)) return rc;
     int grid = (B + GHD_WARPS - 1) / GHD_WARPS;
     const int cap = sm_count() * 4;
     if (grid > cap) grid = cap;
-    kern<<<grid, GHD_WARPS * 32, smem, st>>>(G, Wfc, bias_node, types, H, F, h, out, act, B);
+    kern<<<grid, GHD_WARPS * 32, smem, st>>>(G_dev, Wfc, bias_node, types, H, n_types, h, out, act, B);
     SD_LAUNCH_OK("gru_head_kernel");
     return SD_OK;
 }
 
-bool gru_head_supported(int N, int H, int F) { return (N == 16 || N == 17 || N == 21) && F >= 1 && F <= 4 && H <= 256; }
+bool gru_head_supported(int N, int H, int F) { return (N == 16 || N == 17 || N == 21) && F >= 1 && F <= 3 && H <= 512; }
 
-int gru_head_fp32(const float* G_host, const float* Wfc, const float* bias_node, const NodeTypes& types, int N, int H, int F,
+// G_dev: fc's normalised graph influence [N][N] on the device, or null for the identity
+int gru_head_fp32(const float* G_dev, const float* Wfc, const float* bias_node, const NodeTypes& types, int n_types, int N, int H, int F,
                   const View& h, const ViewW& out, int act, int B, cudaStream_t st) {
     if (B <= 0) return SD_OK;
-    if (N == 21) return ghd_launch<21>(G_host, Wfc, bias_node, types, H, F, h, out, act, B, st);
-    if (N == 16) return ghd_launch<16>(G_host, Wfc, bias_node, types, H, F, h, out, act, B, st);
-    if (N == 17) return ghd_launch<17>(G_host, Wfc, bias_node, types, H, F, h, out, act, B, st);
+#define SD_GHD(NN) if (N == NN) { \
+        if (F == 3) return ghd_launch<NN, 3>(G_dev, Wfc, bias_node, types, n_types, H, h, out, act, B, st); \
+        if (F == 2) return ghd_launch<NN, 2>(G_dev, Wfc, bias_node, types, n_types, H, h, out, act, B, st); \
+        return ghd_launch<NN, 1>(G_dev, Wfc, bias_node, types, n_types, H, h, out, act, B, st); }
+    SD_GHD(21) SD_GHD(16) SD_GHD(17)
+#undef SD_GHD
     set_error("gru_head: %d nodes not instantiated", N);
     return SD_ERR_UNSUPPORTED;
 }

@@ -153,6 +153,15 @@ class LatentDiffusion(nn.Module):
     get_white_noise = get_noise
     get_start_noise = get_noise
 
+    def fill_noise_(self, out: torch.Tensor, offset: int = 0) -> torch.Tensor:
+        """White N(0, I) written into an existing contiguous fp32 CUDA tensor (same Philox stream as get_noise)."""
+        nv.require_cuda(out, "noise")
+        assert out.dtype == torch.float32 and out.is_contiguous()
+        seed = (torch.initial_seed() + 0x9E3779B97F4A7C15 * (self._noise_calls + 1)) & 0xFFFFFFFFFFFFFFFF
+        self._noise_calls += 1
+        nv.check(nv.load().sd_fill_normal(out.data_ptr(), out.numel(), seed, int(offset), nv.stream_ptr(out.device)), "sd_fill_normal")
+        return out
+
     # ------------------------------------------------------------------ network interface
     def feed_model(self, x, t, x_self_cond=None, x_cond=None):
         if self.condition:

@@ -15,7 +15,9 @@ from .autoencoder import AutoEncoder
 from .diffusion import NonisotropicGaussianDiffusion, get_cov_from_corr
 from .network import Denoiser
 
-__all__ = ["DiffusionManager", "get_diffusion_latent_codes", "decode_latent_pred", "get_prediction",
+from .plan import params_key
+
+__all__ = ["DiffusionManager", "get_diffusion_latent_codes", "decode_latent_pred", "get_prediction", "GraphedPrediction",
            "shard_windows", "build_models"]
 
 
@@ -80,6 +82,75 @@ def get_prediction(obs, model, num_samples=50, pred_length=100, **kwargs):
     """obs [W, T_obs, N, 3] -> predictions [W, num_samples, pred_length, N, 3] (eval_prepare_model.py:118-121)."""
     lat_pred, z_past = get_diffusion_latent_codes(obs, model, num_samples=num_samples, **kwargs)
     return decode_latent_pred(obs, lat_pred, z_past, model, num_samples=num_samples, pred_length=pred_length, **kwargs)
+
+
+class GraphedPrediction:
+    """`get_prediction` for a fixed (windows, num_samples, pred_length) captured ONCE as one CUDA graph: encode, the T-step
+    sampling loop (T x (Denoiser kernels + reverse step)) and the decode of every frame -- about 1 100 kernel launches for the
+    AMASS configuration -- are replayed with a single cudaGraphLaunch (north_star item 3; the reference's caller is
+    src/eval_prepare_model.py:118-121).  Fresh noise is drawn by two Philox launches in front of every replay (or injected);
+    observations are copied into the graph's static input.  The capture holds references to the packed plans it baked in and
+    is rebuilt when a parameter or buffer of the models changes (load_state_dict, optimizer step, .to())."""
+
+    def __init__(self, model, windows: int, num_samples: int = 50, pred_length: int = 100, device=None):
+        self.model, self.W, self.S, self.ph = model, int(windows), int(num_samples), int(pred_length)
+        ae, diff = model
+        self.device = torch.device(device) if device is not None else diff.betas.device
+        self._graph = None
+        self._key = None
+
+    def _models_key(self):
+        ae, diff = self.model
+        return (params_key(list(ae.parameters()) + list(ae.buffers()) + list(diff.parameters()) + list(diff.buffers())), diff.precision)
+
+    def _capture(self, obs_shape):
+        ae, diff = self.model
+        dev = self.device
+        N, D, T = diff.channels, diff.seq_length, diff.num_timesteps
+        B = self.W * self.S
+        st = dict(obs=torch.zeros(obs_shape, device=dev, dtype=torch.float32),
+                  start=torch.zeros(B, N, D, device=dev, dtype=torch.float32),
+                  noise=torch.zeros(B, max(T - 1, 1), N, D, device=dev, dtype=torch.float32)[:, :T - 1])
+
+        def run():
+            return get_prediction(st["obs"], self.model, num_samples=self.S, pred_length=self.ph, diffusion_conditioning=True,
+                                  sampler_kwargs=dict(start_noise=st["start"], sampling_noise=st["noise"] if T > 1 else None))
+
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                  # warm-up outside the capture: plans, workspaces, function attributes
+            run()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            st["pred"] = run()
+        self._graph, self._static, self._key = graph, st, self._models_key()
+        self._plans = (ae, diff, diff.model.plan(), diff._diffusion_plan())      # keep what the graph baked in alive
+
+    @torch.no_grad()
+    def __call__(self, obs: torch.Tensor, start_noise: Optional[torch.Tensor] = None, sampling_noise: Optional[torch.Tensor] = None,
+                 clone: bool = False) -> torch.Tensor:
+        """obs [W, T_obs, N, 3] -> predictions [W, S, pred_length, N, 3] (the graph's static output buffer unless clone=True)."""
+        ae, diff = self.model
+        if obs.shape[0] != self.W:
+            raise ValueError(f"graph was built for {self.W} windows, got {obs.shape[0]}")
+        if self._graph is None or self._key != self._models_key() or tuple(self._static["obs"].shape) != tuple(obs.shape):
+            self._graph = None
+            self._capture(tuple(obs.shape))
+        st = self._static
+        st["obs"].copy_(obs, non_blocking=True)
+        if start_noise is not None:
+            st["start"].copy_(start_noise)
+        else:
+            diff.fill_noise_(st["start"])
+        if st["noise"].numel():
+            if sampling_noise is not None:
+                st["noise"].copy_(sampling_noise)
+            else:
+                diff.fill_noise_(st["noise"])
+        self._graph.replay()
+        return st["pred"].clone() if clone else st["pred"]
 
 
 def shard_windows(num_windows: int, rank: int, world_size: int) -> Tuple[int, int]:

@@ -69,3 +69,12 @@ README_CFG = dict(dim=96, cond_dim=0, depth=1, attn_heads=4, attn_dim_head=32, n
 def rel_err(a, b):
     """max |a-b| / max |b|  (the 'relative' of the <=1e-4 fp32 gate: relative to the tensor's scale)."""
     return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+def elementwise_err(a, b, floor=1e-3):
+    """Element-wise statistic next to rel_err: max and 99.9th percentile of |a-b| / max(|b|, floor).  The floor keeps elements
+    near zero (tanh-bounded latents and poses cross zero) from dividing a 1e-7 rounding difference by 1e-9."""
+    a, b = a.double().reshape(-1), b.double().reshape(-1)
+    e = (a - b).abs() / b.abs().clamp_min(floor)
+    k = max(1, int(0.999 * e.numel()))
+    return float(e.max()), float(e.kthvalue(k).values)
