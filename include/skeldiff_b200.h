@@ -223,6 +223,23 @@ int  sd_decode(const sd_glin* initial_hidden, const sd_gru* cell, const sd_glin*
 int  sd_motion_metrics(const float* pred_dev, const float* target_dev, int windows, int samples, int frames, int feat,
                        float scale, float* ade_dev, float* fde_dev, float* apd_dev, void* stream);
 
+/* MMADE / MMFDE per observed window -- replaces mmade / mmfde (src/metrics/multimodal.py:105-120, :122-135) on
+ * transform_to_metric_space(pred): for every multimodal ground truth g of window i the minimum over the window's samples of
+ * the mean (MMADE) / last-frame (MMFDE) L2 distance to g, then the mean over the window's ground truths (0 for a window
+ * without any).  mm_gt_dev [n_gt, frames, feat]: all ground truths, window by window; gt_window_dev [n_gt]: window of each;
+ * gt_offsets_dev [windows + 1]: range of each window in mm_gt_dev; scratch_dev: 2 * n_gt floats.  pred_dev as for sd_motion_metrics. */
+int  sd_multimodal_metrics(const float* pred_dev, const float* mm_gt_dev, const int32_t* gt_window_dev, const int32_t* gt_offsets_dev,
+                           int windows, int n_gt, int samples, int frames, int feat, float scale, float* mmade_dev, float* mmfde_dev,
+                           float* scratch_dev, void* stream);
+
+/* Best-sample selection of the long-term evaluation -- replaces get_best_sample_idx (src/metrics/utils.py:22-30) in
+ * long_term_prediction_best_every50 (src/eval_utils.py:44-67): per window the sample with the smallest mean per-joint L2
+ * distance to the target segment.  pred_dev [windows, samples, frames, joints, 3], target_dev [windows, frames, joints, 3];
+ * outputs (each optional): best_dev [windows, frames, joints, 3] = scale * chosen sample, tail_dev [windows, keep_frames, joints, 3]
+ * = its last keep_frames frames (the next observation), index_dev [windows].  No host round trip. */
+int  sd_best_sample(const float* pred_dev, const float* target_dev, int windows, int samples, int frames, int joints, int keep_frames,
+                    float scale, float* best_dev, float* tail_dev, int32_t* index_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -308,3 +308,23 @@ def fde(target: Tensor, pred: Tensor) -> Tensor:
     w, s, t = pred.shape[:3]
     d = torch.linalg.norm(pred.reshape(w, s, t, -1) - target.reshape(w, 1, t, -1), dim=-1)[..., -1]
     return d.min(-1).values
+
+
+def mmade(pred: Tensor, mm_gt) -> Tensor:
+    """src/metrics/multimodal.py:105-120: per window, mean over its multimodal ground truths of the min-over-samples ADE."""
+    out = torch.zeros(pred.shape[0])
+    for i in range(pred.shape[0]):
+        p = pred[i].reshape(pred.shape[1], pred.shape[2], -1).unsqueeze(0)
+        gt = mm_gt[i].reshape(mm_gt[i].shape[0], pred.shape[2], -1).unsqueeze(1)
+        out[i] = torch.linalg.norm(p - gt, dim=-1).mean(-1).min(-1).values.mean()
+    return out
+
+
+def mmfde(pred: Tensor, mm_gt) -> Tensor:
+    """src/metrics/multimodal.py:122-135: as mmade with the last frame's distance."""
+    out = torch.zeros(pred.shape[0])
+    for i in range(pred.shape[0]):
+        p = pred[i].reshape(pred.shape[1], pred.shape[2], -1).unsqueeze(0)
+        gt = mm_gt[i].reshape(mm_gt[i].shape[0], pred.shape[2], -1).unsqueeze(1)
+        out[i] = torch.linalg.norm(p - gt, dim=-1)[..., -1].min(-1).values.mean()
+    return out

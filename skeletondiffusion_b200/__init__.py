@@ -6,9 +6,9 @@ include/skeldiff_b200.h.  There is no CPU fallback."""
 from .diffusion import NonisotropicGaussianDiffusion, LatentDiffusion, get_cov_from_corr
 from .network import Denoiser, StaticGraphLinear, Attention, ResnetBlock, Residual, PreNorm, RMSNorm
 from .autoencoder import AutoEncoder, Encoder, Decoder, StaticGraphGRU
-from .pipeline import (DiffusionManager, GraphedPrediction, get_prediction, get_diffusion_latent_codes, decode_latent_pred,
+from .pipeline import (DiffusionManager, GraphedPrediction, best_sample, long_term_prediction_best_every50, get_prediction, get_diffusion_latent_codes, decode_latent_pred,
                        shard_windows, build_models)
 from .skeletons import get_skeleton, SkeletonSpec
-from .metrics import motion_metrics, ade, fde, apd
+from .metrics import motion_metrics, multimodal_metrics, ade, fde, apd, mmade, mmfde
 
 __version__ = "0.1.0"

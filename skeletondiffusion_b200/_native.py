@@ -69,6 +69,8 @@ SIGNATURES = {
     "sd_sample_loop": (_I, [_P, _P, _P, C.POINTER(SdView), _P, _P, _I, _I, _P, _I, _P]),
     "sd_fill_normal": (_I, [_P, _I64, _U64, _U64, _P]),
     "sd_motion_metrics": (_I, [_P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P]),
+    "sd_best_sample": (_I, [_P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P]),
+    "sd_multimodal_metrics": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P]),
     "sd_gru_create": (_I, [_I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, C.POINTER(_P)]),
     "sd_gru_set_fused": (_I, [_P, _P, _P, _P, _P]),
     "sd_gru_set_bf16x3": (_I, [_P, _P]),

@@ -513,6 +513,26 @@ int sd_motion_metrics(const float* pred_dev, const float* target_dev, int window
     return motion_metrics_fp32(pred_dev, target_dev, windows, samples, frames, feat, scale, ade_dev, fde_dev, apd_dev, static_cast<cudaStream_t>(stream));
 }
 
+int sd_multimodal_metrics(const float* pred_dev, const float* mm_gt_dev, const int32_t* gt_window_dev, const int32_t* gt_offsets_dev,
+                          int windows, int n_gt, int samples, int frames, int feat, float scale, float* mmade_dev, float* mmfde_dev,
+                          float* scratch_dev, void* stream) {
+    if (windows == 0) return SD_OK;
+    if (windows < 0 || n_gt < 0 || samples < 1 || frames < 1 || feat < 1) { set_error("sd_multimodal_metrics: bad shape"); return SD_ERR_INVALID; }
+    if (!pred_dev || !gt_offsets_dev || !(mmade_dev || mmfde_dev) || (n_gt > 0 && (!mm_gt_dev || !gt_window_dev || !scratch_dev))) {
+        set_error("sd_multimodal_metrics: null argument"); return SD_ERR_INVALID;
+    }
+    return multimodal_metrics_fp32(pred_dev, mm_gt_dev, gt_window_dev, gt_offsets_dev, windows, n_gt, samples, frames, feat, scale,
+                                   mmade_dev, mmfde_dev, scratch_dev, static_cast<cudaStream_t>(stream));
+}
+
+int sd_best_sample(const float* pred_dev, const float* target_dev, int windows, int samples, int frames, int joints, int keep_frames,
+                   float scale, float* best_dev, float* tail_dev, int32_t* index_dev, void* stream) {
+    if (windows == 0) return SD_OK;
+    if (windows < 0 || samples < 1 || frames < 1 || joints < 1 || !pred_dev || !target_dev) { set_error("sd_best_sample: invalid arguments"); return SD_ERR_INVALID; }
+    return best_sample_fp32(pred_dev, target_dev, windows, samples, frames, joints, keep_frames, scale, best_dev, tail_dev, index_dev,
+                            static_cast<cudaStream_t>(stream));
+}
+
 size_t sd_sample_workspace_bytes(const sd_diffusion* df, const sd_denoiser* dn, int batch, int precision) {
     if (!df || !dn || batch <= 0) return 0;
     const size_t lat = align_up((size_t)batch * df->N * df->D * sizeof(float));

@@ -79,7 +79,10 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) 
 // (hi16 of b) << 16 | (hi16 of a): two bf16 packed in element order a, b
 __device__ __forceinline__ uint32_t pack_hi(uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x7632); }
 
-template <int ACT, bool HAS_RES>
+// FAST: tanh through MUFU.EX2 + MUFU.RCP (tc::tanh_ex2, ~1e-7 absolute) instead of libdevice tanhf (SKELDIFF_ACCURATE_EPILOGUE=1)
+template <bool FAST> __device__ __forceinline__ float t3_tanh(float x) { return FAST ? tanh_ex2(x) : tanhf(x); }
+
+template <int ACT, bool HAS_RES, bool FAST>
 __global__ void __launch_bounds__(T3_THREADS, 1)
 glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -247,6 +250,7 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
                                 const bool main_pair = (pa + pw == 0);
 #pragma unroll
                                 for (int k = 0; k < T3_BK / 16; ++k) {
+                                    if (kb * T3_BK + 16 * k >= p.K) continue;        // zero tail of a partly filled last k-block (K = 96)
                                     uint32_t& first = main_pair ? first_main : first_corr;
                                     umma_bf16(main_pair ? d_main : d_corr, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, first ? 0u : 1u);
                                     first = 0u;
@@ -374,10 +378,10 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
                     if (pre_base) { x.x += pp[j].x; x.y += pp[j].y; x.z += pp[j].z; x.w += pp[j].w; }
                     o[j].x = fmaf(x.x, m4.x, a4.x); o[j].y = fmaf(x.y, m4.y, a4.y);
                     o[j].z = fmaf(x.z, m4.z, a4.z); o[j].w = fmaf(x.w, m4.w, a4.w);
-                    if (ACT == SD_ACT_TANH) { o[j].x = tanhf(o[j].x); o[j].y = tanhf(o[j].y); o[j].z = tanhf(o[j].z); o[j].w = tanhf(o[j].w); }
+                    if (ACT == SD_ACT_TANH) { o[j].x = t3_tanh<FAST>(o[j].x); o[j].y = t3_tanh<FAST>(o[j].y); o[j].z = t3_tanh<FAST>(o[j].z); o[j].w = t3_tanh<FAST>(o[j].w); }
                     if (ACT == SD_ACT_TANH_TANH) {
-                        o[j].x = tanhf(tanhf(o[j].x)); o[j].y = tanhf(tanhf(o[j].y));
-                        o[j].z = tanhf(tanhf(o[j].z)); o[j].w = tanhf(tanhf(o[j].w));
+                        o[j].x = t3_tanh<FAST>(t3_tanh<FAST>(o[j].x)); o[j].y = t3_tanh<FAST>(t3_tanh<FAST>(o[j].y));
+                        o[j].z = t3_tanh<FAST>(t3_tanh<FAST>(o[j].z)); o[j].w = t3_tanh<FAST>(t3_tanh<FAST>(o[j].w));
                     }
                     if (HAS_RES) { o[j].x += rr[j].x; o[j].y += rr[j].y; o[j].z += rr[j].z; o[j].w += rr[j].w; }
                 }
@@ -435,9 +439,10 @@ bool glin_tc3_supported(int K0, int K1, int OUT) {
     return t3_pick_bn(K0 + K1, OUT) != 0;
 }
 
-template <int ACT, bool HAS_RES>
+template <int ACT, bool HAS_RES, bool FAST = false>
 static int t3_launch_t(const CUtensorMap& mw, const T3Params& p, int grid, size_t smem, cudaStream_t st) {
-    auto kern = glin_tc3_kernel<ACT, HAS_RES>;
+    if (ACT != SD_ACT_NONE && !FAST && fast_epilogue()) return t3_launch_t<ACT, HAS_RES, ACT != SD_ACT_NONE>(mw, p, grid, smem, st);
+    auto kern = glin_tc3_kernel<ACT, HAS_RES, FAST>;
     static unsigned long long configured = 0;      // bit d: attribute set on device d (it is per device)
     if (int rc_attr = opt_in_smem(kern, (size_t)((227 * 1024)), configured)) return rc_attr;
     kern<<<grid, T3_THREADS, smem, st>>>(mw, p);

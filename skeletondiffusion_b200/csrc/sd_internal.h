@@ -82,9 +82,14 @@ int reverse_step_fp32(const sd_diffusion* d, const float* x_t, const float* x0, 
 int time_table_fp32(const float* times, int rows, int C, float theta, int time_dim, const float* w1, const float* b1,
                     const float* w3, const float* b3, const float* const* head_w, const float* const* head_b,
                     int n_heads, float* table, float* ws, cudaStream_t st);
+bool fast_epilogue();   // tanh / sigmoid of the fp32-grade tensor-core path through MUFU.EX2 + MUFU.RCP (default) or libdevice (SKELDIFF_ACCURATE_EPILOGUE=1)
 int fill_normal(float* out, long long count, uint64_t seed, uint64_t offset, cudaStream_t st);
 int motion_metrics_fp32(const float* pred, const float* target, int windows, int samples, int frames, int feat, float scale,
                         float* ade, float* fde, float* apd, cudaStream_t st);
+int multimodal_metrics_fp32(const float* pred, const float* mm_gt, const int* gt_window, const int* gt_offsets, int windows, int n_gt,
+                            int samples, int frames, int feat, float scale, float* mmade, float* mmfde, float* scratch, cudaStream_t st);
+int best_sample_fp32(const float* pred, const float* target, int windows, int samples, int frames, int joints, int keep, float scale,
+                     float* best, float* tail, int* index, cudaStream_t st);
 int q_sample_fp32(const float* x0, const float* eps, const int* t, const float* sqrt_ac, const float* M, float* out,
                   int B, int N, int D, cudaStream_t st);
 int mahalanobis_loss_fp32(const float* out, const float* x0, const int* t, const float* S, float* loss,

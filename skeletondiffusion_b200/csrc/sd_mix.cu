@@ -29,18 +29,12 @@ constexpr int PSK_WARPS = 12;                  // all compute (ptxas budgets reg
 constexpr int PSK_THREADS = PSK_WARPS * 32;
 constexpr int PSK_SMEM = 200 * 1024;           // ring bytes per CTA (all warps)
 
-// tanh with ~1e-7 absolute error in 7 instructions: (1 - t) / (1 + t), t = exp(-2|x|) (MUFU.EX2 + MUFU.RCP, no branch).
-// Its consumers are linear layers, so the ABSOLUTE error is what propagates; it equals the rounding of a value of magnitude 1.
-__device__ __forceinline__ float smix_tanh(float x) {
-    const float t = exp2f(-2.8853900817779268f * fabsf(x));
-    return copysignf(__fdividef(1.0f - t, 1.0f + t), x);
-}
 // FAST: tanh / sigmoid through MUFU.EX2 + MUFU.RCP (absolute error ~1e-7) instead of libdevice (SKELDIFF_ACCURATE_EPILOGUE=1 selects libdevice)
-template <bool FAST> __device__ __forceinline__ float mix_tanh(float x) { return FAST ? smix_tanh(x) : tanhf(x); }
+template <bool FAST> __device__ __forceinline__ float mix_tanh(float x) { return FAST ? tc::tanh_ex2(x) : tanhf(x); }
 template <bool FAST> __device__ __forceinline__ float mix_sigmoid(float v) {
     return FAST ? __fdividef(1.0f, 1.0f + exp2f(-1.4426950408889634f * v)) : 1.0f / (1.0f + expf(-v));
 }
-static bool fast_epilogue() {
+bool fast_epilogue() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("SKELDIFF_ACCURATE_EPILOGUE"); v = (e && e[0] == '1') ? 0 : 1; }
     return v == 1;
@@ -106,20 +100,35 @@ sample_mix_kernel(const __grid_constant__ MixMat<N> G, const __grid_constant__ C
     const int my_samples = (int)blockIdx.x < p.B ? (p.B - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const int items = my_samples * chunks;                            // this CTA's items; warp w takes w, w + WARPS, ...
     const int n_my = items > warp ? (items - 1 - warp) / PSK_WARPS + 1 : 0;
-    auto issue = [&](int j) {
+    // the mixed bias [N][OUT] is read once per item and output: kept in shared memory when it fits (a global load per use
+    // left the warps waiting on the L1 / L2 round trip: 33 % of the stall samples of the first version were these FADDs)
+    float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint64_t*>(psk_smem + (size_t)PSK_WARPS * p.slots * BOX) + PSK_WARPS * p.slots);
+    if (p.bias_node) {                                                // (the launcher guarantees that the table fits)
+        for (int i = threadIdx.x; i < N * p.OUT; i += PSK_THREADS) bias_s[i] = __ldg(p.bias_node + i);
+        __syncthreads();
+    }
+    // position of the next box to fetch, advanced incrementally (no divisions in the loop)
+    int is_j = 0, is_k = warp / chunks, is_c = warp - is_k * chunks, is_slot = 0;
+    const int dk = PSK_WARPS / chunks, dc = PSK_WARPS - dk * chunks;
+    auto issue = [&]() {
         tc::fence_proxy_async();
         __syncwarp();
-        if (j < n_my && lane == 0) {
-            const int item = warp + j * PSK_WARPS, k = item / chunks, c0 = (item - k * chunks) * (32 * COLS);
-            uint64_t* bar = &ring.full[j % ring.slots];
+        if (is_j < n_my && lane == 0) {
+            uint64_t* bar = &ring.full[is_slot];
             tc::mbar_arrive_expect_tx(bar, (uint32_t)BOX * 4u);
-            tc::tma_load_3d(ring.slot_ptr(j), &map_y, bar, c0, 0, (int)blockIdx.x + k * (int)gridDim.x);
+            tc::tma_load_3d(ring.buf + (size_t)is_slot * BOX, &map_y, bar, is_c * (32 * COLS), 0, (int)blockIdx.x + is_k * (int)gridDim.x);
         }
+        ++is_j;
+        is_k += dk; is_c += dc;
+        if (is_c >= chunks) { is_c -= chunks; ++is_k; }
+        if (++is_slot == ring.slots) is_slot = 0;
     };
-    for (int j = 0; j < p.slots - 1; ++j) issue(j);
+    for (int j = 0; j < p.slots - 1; ++j) issue();
+    int k = warp / chunks, cc = warp - k * chunks, slot = 0;
+    uint32_t phase = 0;
     for (int j = 0; j < n_my; ++j) {
-        issue(j + p.slots - 1);                                       // refills the slot whose box was read in the previous iteration
-        const int item = warp + j * PSK_WARPS, k = item / chunks, c = (item - k * chunks) * (32 * COLS) + lane;
+        issue();                                                      // refills the slot whose box was read in the previous iteration
+        const int c = cc * (32 * COLS) + lane;
         const int b = (int)blockIdx.x + k * (int)gridDim.x;
         float res[N][COLS];
         if (HAS_RES) {                                                // the residual row segments are in flight during the mix
@@ -135,8 +144,8 @@ sample_mix_kernel(const __grid_constant__ MixMat<N> G, const __grid_constant__ C
             mul[q] = p.ss ? __ldg(p.ss + c + 32 * q) + 1.0f : 1.0f;
             add[q] = p.ss ? __ldg(p.ss + p.OUT + c + 32 * q) : 0.0f;
         }
-        ring.acquire(j);
-        const float* ys = ring.slot_ptr(j) + lane;                    // box [N][32 * COLS]
+        tc::mbar_wait(&ring.full[slot], phase, j);
+        const float* ys = ring.buf + (size_t)slot * BOX + lane;       // box [N][32 * COLS]
         float in[N][COLS];
 #pragma unroll
         for (int m = 0; m < N; ++m)
@@ -159,13 +168,16 @@ sample_mix_kernel(const __grid_constant__ MixMat<N> G, const __grid_constant__ C
 #pragma unroll
             for (int q = 0; q < COLS; ++q) {
                 float v = acc[n][q];
-                if (p.bias_node) v += __ldg(p.bias_node + n * p.OUT + c + 32 * q);
+                if (p.bias_node) v += bias_s[n * p.OUT + c + 32 * q];
                 v = fmaf(v, mul[q], add[q]);
                 if (ACT == SD_ACT_TANH) v = mix_tanh<FAST>(v);
                 if (ACT == SD_ACT_TANH_TANH) v = mix_tanh<FAST>(mix_tanh<FAST>(v));
                 if (HAS_RES) v += res[n][q];
                 ob[(long long)n * p.out.sn + 32 * q] = v;
             }
+        k += dk; cc += dc;
+        if (cc >= chunks) { cc -= chunks; ++k; }
+        if (++slot == ring.slots) { slot = 0; phase ^= 1u; }
     }
 }
 
@@ -186,7 +198,9 @@ static int smix_launch_c(const float* G_host, const float* y, const SmixParams& 
         const cuuint32_t box[3] = {(cuuint32_t)(32 * COLS), (cuuint32_t)N, 1};
         if (int rc = psk_map(&map_y, y, 3, dims, strides, box)) return rc;
     }
-    const size_t smem = (size_t)PSK_WARPS * slots * (box_bytes + 8) + 128;
+    const size_t bias_bytes = p.bias_node ? (size_t)N * p.OUT * 4 : 0;
+    if (bias_bytes > 24 * 1024) { set_error("sample_mix: bias table of %zu bytes does not fit shared memory", bias_bytes); return SD_ERR_UNSUPPORTED; }
+    const size_t smem = (size_t)PSK_WARPS * slots * (box_bytes + 8) + bias_bytes + 128;
     auto kern = sample_mix_kernel<N, ACT, HAS_RES, COLS, FAST>;
     static unsigned long long configured = 0;
     if (int rc = opt_in_smem(kern, 227 * 1024, configured)) return rc;
@@ -222,6 +236,7 @@ bool sample_mix_supported(int N, int OUT, const float* y, const Epilogue& epi, c
     if (off) return false;
     if (!(N == 16 || N == 17 || N == 21)) return false;
     if (OUT % 32 || OUT <= 0) return false;
+    if (epi.bias_node && (size_t)N * OUT * 4 > 24 * 1024) return false;   // the mixed bias table lives in shared memory
     if (reinterpret_cast<uintptr_t>(y) & 15u) return false;
     if (epi.ss_row_idx || out.rep != 1) return false;                 // per-sample time rows: generic kernel
     return true;
@@ -282,87 +297,99 @@ gru_sample_kernel(const __grid_constant__ MixMat<N> G, const __grid_constant__ C
     const int my_samples = (int)blockIdx.x < p.B ? (p.B - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const int items = my_samples * chunks;
     const int n_my = items > warp ? (items - 1 - warp) / PSK_WARPS + 1 : 0;
-    const int n_boxes = n_my * BPI;
     const int H3 = 3 * p.H;
-    // box j of this warp: item j / 7, part j % 7 = (hr_r, xr_r, hr_z, xr_z, hr_n, xr_n, h)
-    auto issue = [&](int j) {
+    // next box to fetch: (item k / chunk c, part); parts in consumption order hr_r, xr_r, hr_z, xr_z, hr_n, xr_n, h
+    int is_it = 0, is_part = 0, is_k = warp / chunks, is_c = warp - is_k * chunks, is_slot = 0;
+    const int dk = PSK_WARPS / chunks, dc = PSK_WARPS - dk * chunks;
+    auto issue = [&]() {
         tc::fence_proxy_async();
         __syncwarp();
-        if (j < n_boxes && lane == 0) {
-            const int it = j / BPI, part = j - it * BPI;
-            const int item = warp + it * PSK_WARPS, k = item / chunks, c0 = (item - k * chunks) * 32;
-            const int b = (int)blockIdx.x + k * (int)gridDim.x;
-            uint64_t* bar = &ring.full[j % ring.slots];
+        if (is_it < n_my && lane == 0) {
+            const int b = (int)blockIdx.x + is_k * (int)gridDim.x;
+            uint64_t* bar = &ring.full[is_slot];
+            float* dst = ring.buf + (size_t)is_slot * BOX;
             tc::mbar_arrive_expect_tx(bar, (uint32_t)BOX * 4u);
-            if (part == 6) tc::tma_load_3d(ring.slot_ptr(j), &map_h, bar, c0, 0, b);
-            else tc::tma_load_4d(ring.slot_ptr(j), (part & 1) ? &map_xr : &map_hr, bar, c0, part >> 1, 0, b);
+            if (is_part == 6) tc::tma_load_3d(dst, &map_h, bar, is_c * 32, 0, b);
+            else tc::tma_load_4d(dst, (is_part & 1) ? &map_xr : &map_hr, bar, is_c * 32, is_part >> 1, 0, b);
         }
+        if (++is_part == BPI) {
+            is_part = 0; ++is_it;
+            is_k += dk; is_c += dc;
+            if (is_c >= chunks) { is_c -= chunks; ++is_k; }
+        }
+        if (++is_slot == ring.slots) is_slot = 0;
     };
-    for (int j = 0; j < p.slots - 1; ++j) issue(j);
-    int jb = 0;                                                       // next box to consume
+    for (int j = 0; j < p.slots - 1; ++j) issue();
+    int k = warp / chunks, cc = warp - k * chunks, slot = 0;
+    uint32_t phase = 0;
+    // consume one box: refill the slot freed one box earlier, then wait for this one
+    auto take = [&]() -> const float* {
+        issue();
+        tc::mbar_wait(&ring.full[slot], phase, k);
+        const float* ptr = ring.buf + (size_t)slot * BOX + lane;
+        if (++slot == ring.slots) { slot = 0; phase ^= 1u; }
+        return ptr;
+    };
     for (int it = 0; it < n_my; ++it) {
-        const int item = warp + it * PSK_WARPS, k = item / chunks, u = (item - k * chunks) * 32 + lane;
+        const int u = cc * 32 + lane;
         const long long b = (long long)blockIdx.x + (long long)k * gridDim.x;
         float* ob = p.h_out.ptr + b * p.h_out.sb + u;
-        float in[N][1], acc[N][1], rg[N], zg[N], hp[N];
-        // consume one box: refill the slot freed one box earlier, then wait for this one
-        auto take = [&]() -> const float* {
-            issue(jb + p.slots - 1);
-            ring.acquire(jb);
-            return ring.slot_ptr(jb++) + lane;
-        };
+        // Two passes over G with TWO columns each: (r, z) then (hr_n, xr_n).  One pass with four columns needs 168 registers
+        // for the inputs and accumulators alone; four passes of one column re-read G four times and, unrolled or as a
+        // predicated loop, cost 5 300 instructions per item (ncu) against ~3 000 here.
+        float in[N][2], acc[N][2], rg[N], zg[N], hp[N];
 #pragma unroll 1
-        for (int ph = 0; ph < 4; ++ph) {
-            // phases 0, 1: hr_g + xr_g (the mix is linear); 2: hr_n; 3: xr_n, then h
-            const float* s0 = take();
+        for (int pass = 0; pass < 2; ++pass) {
+            {
+                const float* s0 = take();                             // hr_r | hr_n
 #pragma unroll
-            for (int n = 0; n < N; ++n) in[n][0] = s0[n * 32];
-            if (ph < 2) {
-                const float* s1 = take();
+                for (int n = 0; n < N; ++n) in[n][0] = s0[n * 32];
+                const float* s1 = take();                             // xr_r | xr_n
+                if (pass == 0) {
 #pragma unroll
-                for (int n = 0; n < N; ++n) in[n][0] += s1[n * 32];
+                    for (int n = 0; n < N; ++n) in[n][0] += s1[n * 32];
+                    const float* s2 = take();                         // hr_z
+#pragma unroll
+                    for (int n = 0; n < N; ++n) in[n][1] = s2[n * 32];
+                    const float* s3 = take();                         // xr_z
+#pragma unroll
+                    for (int n = 0; n < N; ++n) in[n][1] += s3[n * 32];
+                } else {
+#pragma unroll
+                    for (int n = 0; n < N; ++n) in[n][1] = s1[n * 32];
+                    const float* s2 = take();                         // h
+#pragma unroll
+                    for (int n = 0; n < N; ++n) hp[n] = s2[n * 32];
+                }
             }
-            if (ph == 3) {
-                const float* s2 = take();
-#pragma unroll
-                for (int n = 0; n < N; ++n) hp[n] = s2[n * 32];
-            }
-            if (MIX) mix_nodes<N, 1>(G, in, acc);
+            if (MIX) mix_nodes<N, 2>(G, in, acc);
             else {
 #pragma unroll
-                for (int n = 0; n < N; ++n) acc[n][0] = in[n][0];
+                for (int n = 0; n < N; ++n) { acc[n][0] = in[n][0]; acc[n][1] = in[n][1]; }
             }
-            if (ph == 0) {
+            if (pass == 0) {
 #pragma unroll
                 for (int n = 0; n < N; ++n) {
-                    float v = acc[n][0];
-                    if (p.bias_x) v += __ldg(p.bias_x + n * H3 + u) + __ldg(p.bias_h + n * H3 + u);
-                    rg[n] = mix_sigmoid<FAST>(v);
-                }
-            } else if (ph == 1) {
-#pragma unroll
-                for (int n = 0; n < N; ++n) {
-                    float v = acc[n][0];
-                    if (p.bias_x) v += __ldg(p.bias_x + n * H3 + p.H + u) + __ldg(p.bias_h + n * H3 + p.H + u);
-                    zg[n] = mix_sigmoid<FAST>(v);
-                }
-            } else if (ph == 2) {
-#pragma unroll
-                for (int n = 0; n < N; ++n) {
-                    float v = acc[n][0];
-                    if (p.bias_h) v += __ldg(p.bias_h + n * H3 + 2 * p.H + u);
-                    rg[n] *= v;                                       // r * hr_n
+                    float vr = acc[n][0], vz = acc[n][1];
+                    if (p.bias_x) {
+                        vr += __ldg(p.bias_x + n * H3 + u) + __ldg(p.bias_h + n * H3 + u);
+                        vz += __ldg(p.bias_x + n * H3 + p.H + u) + __ldg(p.bias_h + n * H3 + p.H + u);
+                    }
+                    rg[n] = mix_sigmoid<FAST>(vr);
+                    zg[n] = mix_sigmoid<FAST>(vz);
                 }
             } else {
 #pragma unroll
                 for (int n = 0; n < N; ++n) {
-                    float v = acc[n][0] + rg[n];
-                    if (p.bias_x) v += __ldg(p.bias_x + n * H3 + 2 * p.H + u);
-                    const float nn = mix_tanh<FAST>(v);
+                    float vh = acc[n][0], vx = acc[n][1];
+                    if (p.bias_x) { vh += __ldg(p.bias_h + n * H3 + 2 * p.H + u); vx += __ldg(p.bias_x + n * H3 + 2 * p.H + u); }
+                    const float nn = mix_tanh<FAST>(vx + rg[n] * vh);
                     ob[(long long)n * p.h_out.sn] = nn - nn * zg[n] + zg[n] * hp[n];
                 }
             }
         }
+        k += dk; cc += dc;
+        if (cc >= chunks) { cc -= chunks; ++k; }
     }
 }
 

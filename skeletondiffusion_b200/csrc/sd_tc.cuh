@@ -128,4 +128,11 @@ __device__ __forceinline__ float tanh_acc(float x) {
     return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f);
 }
 
+// tanh with ~1e-7 ABSOLUTE error in 7 instructions: (1 - t) / (1 + t), t = exp(-2|x|) (MUFU.EX2 + MUFU.RCP, no branch).
+// Its consumers are linear layers, so the absolute error is what propagates; it equals the rounding of a value of magnitude 1.
+__device__ __forceinline__ float tanh_ex2(float x) {
+    const float t = exp2f(-2.8853900817779268f * fabsf(x));
+    return copysignf(__fdividef(1.0f - t, 1.0f + t), x);
+}
+
 }}  // namespace sd::tc

@@ -7,8 +7,9 @@ that all three metrics are linear in: pass it as `scale` to `motion_metrics` ins
 prediction tensor.  CUDA only: there is no CPU fallback (the CPU statement of the metrics lives in the test infrastructure)."""
 from __future__ import annotations
 
+import itertools
 import math
-from typing import Optional, Tuple
+from typing import Optional, Sequence, Tuple
 
 import torch
 
@@ -63,3 +64,38 @@ def fde(target, pred, t0=0, t=-1, reduction="mean", **kwargs):
 
 def apd(pred, t0=0, t=-1, **kwargs):
     return motion_metrics(None, pred, 1.0, t0, t, (False, False, True))[2]
+
+
+def multimodal_metrics(pred: torch.Tensor, mm_gt: Sequence[torch.Tensor], scale: float = 1.0, t0: int = 0, t: int = -1):
+    """(mmade [W], mmfde [W]) of pred [W, S, T, ...] against the ragged multimodal ground truths mm_gt[i] [n_i, T, ...]
+    (src/metrics/multimodal.py:105-135), one launch of the metric kernel over all ground truths."""
+    nv.require_cuda(pred, "pred")
+    pred = _frames(pred, t0, t, 2)
+    W, S, T = pred.shape[:3]
+    F = math.prod(pred.shape[3:])
+    p = pred.reshape(W, S, T, F).to(torch.float32).contiguous()
+    if len(mm_gt) != W:
+        raise ValueError(f"mm_gt must hold one tensor per window ({W}), got {len(mm_gt)}")
+    counts = [int(g.shape[0]) for g in mm_gt]
+    n_gt = sum(counts)
+    dev = p.device
+    offsets = torch.tensor([0] + list(itertools.accumulate(counts)), dtype=torch.int32, device=dev)
+    out_a, out_f = torch.empty(W, device=dev), torch.empty(W, device=dev)
+    if n_gt:
+        gts = torch.cat([_frames(g.to(dev, torch.float32), t0, t, 1).reshape(g.shape[0], T, F) for g in mm_gt if g.shape[0]], 0).contiguous()
+        win = torch.repeat_interleave(torch.arange(W, dtype=torch.int32, device=dev), torch.tensor(counts, device=dev))
+        scratch = torch.empty(2 * n_gt, device=dev)
+    else:
+        gts = win = scratch = None
+    if W:
+        nv.check(nv.load().sd_multimodal_metrics(p.data_ptr(), nv.dptr(gts), nv.dptr(win), offsets.data_ptr(), W, n_gt, S, T, F, float(scale),
+                                                 out_a.data_ptr(), out_f.data_ptr(), nv.dptr(scratch), nv.stream_ptr(dev)), "sd_multimodal_metrics")
+    return out_a, out_f
+
+
+def mmade(target, pred, mm_gt, t0=0, t=-1, **kwargs):
+    return multimodal_metrics(pred, mm_gt, t0=t0, t=t)[0]
+
+
+def mmfde(target, pred, mm_gt, t0=0, t=-1, **kwargs):
+    return multimodal_metrics(pred, mm_gt, t0=t0, t=t)[1]

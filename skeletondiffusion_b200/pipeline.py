@@ -18,7 +18,7 @@ from .network import Denoiser
 from .plan import params_key
 
 __all__ = ["DiffusionManager", "get_diffusion_latent_codes", "decode_latent_pred", "get_prediction", "GraphedPrediction",
-           "shard_windows", "build_models"]
+           "best_sample", "long_term_prediction_best_every50", "shard_windows", "build_models"]
 
 
 class DiffusionManager:
@@ -82,6 +82,57 @@ def get_prediction(obs, model, num_samples=50, pred_length=100, **kwargs):
     """obs [W, T_obs, N, 3] -> predictions [W, num_samples, pred_length, N, 3] (eval_prepare_model.py:118-121)."""
     lat_pred, z_past = get_diffusion_latent_codes(obs, model, num_samples=num_samples, **kwargs)
     return decode_latent_pred(obs, lat_pred, z_past, model, num_samples=num_samples, pred_length=pred_length, **kwargs)
+
+
+def best_sample(pred: torch.Tensor, target: torch.Tensor, keep_frames: int = 0, scale: float = 1.0):
+    """get_best_sample_idx (src/metrics/utils.py:22-30) on the device: per window the sample closest to `target` in mean per-joint
+    distance.  pred [W, S, T, J, 3], target [W, T, J, 3] -> (best [W, T, J, 3], tail [W, keep_frames, J, 3], index [W]),
+    best / tail multiplied by `scale`."""
+    from . import _native as nv
+    nv.require_cuda(pred, "pred")
+    W, S, T, J, F = pred.shape
+    assert F == 3 and tuple(target.shape) == (W, T, J, 3), f"target {tuple(target.shape)} does not match pred {tuple(pred.shape)}"
+    p, tg = pred.float().contiguous(), target.to(pred.device, torch.float32).contiguous()
+    best = torch.empty(W, T, J, 3, device=p.device)
+    tail = torch.empty(W, keep_frames, J, 3, device=p.device)
+    index = torch.empty(W, device=p.device, dtype=torch.int32)
+    nv.check(nv.load().sd_best_sample(p.data_ptr(), tg.data_ptr(), W, S, T, J, keep_frames, float(scale), best.data_ptr(),
+                                      tail.data_ptr() if keep_frames else None, index.data_ptr(), nv.stream_ptr(p.device)), "sd_best_sample")
+    return best, tail, index
+
+
+@torch.no_grad()
+def long_term_prediction_best_every50(data: torch.Tensor, target: torch.Tensor, model, skeleton, num_samples: int = 50,
+                                      pred_length: int = 100, long_term_factor: float = 2.0, sampler_kwargs_per_segment=None,
+                                      predict_fn=None):
+    """Long-term autoregressive evaluation (src/eval_utils.py:44-67): predict `num_samples` continuations, keep per window the
+    one closest to the ground-truth segment, feed its last obs-length frames back in as the next observation, and so on for
+    ceil(long_term_factor) segments (the last one cut to the fractional part).  Everything stays on the device: the
+    reference's per-segment `.cpu()` of the arg-min indices (src/metrics/utils.py:24) is the sd_best_sample kernel.
+    Like the reference (eval_utils.py:58-65 after process_evaluation_pair), the frames fed back are the METRIC-space ones
+    (multiplied by pose_box_size); this is reproduced, not corrected.
+    Returns (target [W, L, J, 3], pred [W, num_samples, L, J, 3] (the chosen continuation repeated), obs in metric space).
+    NB the reference function needs `math` in its module namespace (src/eval_utils.py never imports it)."""
+    import math
+    n_seg = math.ceil(long_term_factor)
+    n_past = data.shape[-3]
+    scale = float(skeleton.pose_box_size)
+    new_data, finals, targets = data, [], []
+    for idx in range(n_seg):
+        kw = {} if sampler_kwargs_per_segment is None else dict(sampler_kwargs=sampler_kwargs_per_segment[idx])
+        if predict_fn is not None:                 # the reference takes the predictor as a callable as well (eval.py:73-74)
+            pred = predict_fn(new_data)
+        else:
+            pred = get_prediction(new_data, model, num_samples=num_samples, pred_length=pred_length, diffusion_conditioning=True, **kw)
+        if idx == n_seg - 1 and int(long_term_factor) != long_term_factor:
+            pred = pred[..., :int(long_term_factor * pred_length) % pred_length, :, :].contiguous()
+        seg = target[..., idx * pred_length:(idx + 1) * pred_length, :, :][..., :pred.shape[2], :, :]
+        best, tail, _ = best_sample(pred, seg.to(pred.device), keep_frames=min(n_past, pred.shape[2]), scale=scale)
+        finals.append(best)
+        targets.append(seg.to(pred.device) * scale)
+        new_data = tail
+    final = torch.cat(finals, dim=-3)
+    return torch.cat(targets, dim=-3), final.unsqueeze(1).repeat(1, num_samples, 1, 1, 1), data * scale
 
 
 class GraphedPrediction:

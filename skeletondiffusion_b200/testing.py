@@ -55,3 +55,21 @@ def synth_state_dict(reference_sd: Dict[str, torch.Tensor], seed: int = 0, mode:
         else:
             raise KeyError(f"synth_state_dict: no rule for '{k}' {shape}")
     return out
+
+
+def fake_predictor(seed: int, num_samples: int, pred_length: int):
+    """Deterministic stand-in for get_prediction used to pin the control flow of the long-term evaluation against the
+    reference's own function: pred[w, s, t] = tanh(mean_frames(obs[w]) * a[s] + b[s, t]) with seeded a, b."""
+    import numpy as np
+    rs = np.random.RandomState(seed)
+    a = torch.from_numpy(rs.uniform(0.5, 1.5, size=(num_samples, 1, 1, 1)).astype("float32"))
+    holder = {}
+
+    def predict(obs: torch.Tensor, **_):
+        W, _t, J, F = obs.shape
+        if "b" not in holder:
+            holder["b"] = torch.from_numpy(np.random.RandomState(seed + 1).normal(0, 0.4, size=(num_samples, pred_length, J, F)).astype("float32"))
+        m = obs.float().mean(dim=1, keepdim=True).unsqueeze(1)                      # [W, 1, 1, J, F]
+        return torch.tanh(m * a.to(obs.device).unsqueeze(0) + holder["b"].to(obs.device).unsqueeze(0)).contiguous()
+
+    return predict

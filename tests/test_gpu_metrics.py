@@ -95,3 +95,66 @@ def test_metrics_properties_at_bench_shape(cuda_device):
     assert float(a4.abs().max()) == 0.0 and float(f4.abs().max()) == 0.0
     same = target[:, None].expand(W, 4, T, 21, 3).contiguous()
     assert float(sdb.apd(same).abs().max()) == 0.0
+
+
+def test_multimodal_metrics_vs_oracle_and_reference_fixture(cuda_device):
+    """MMADE / MMFDE with ragged ground-truth groups (1, several, many per window) against the oracle's statement of
+    src/metrics/multimodal.py:105-135 and against values produced by the reference's own mmade / mmfde (tests/golden/mm_metrics.npz,
+    made by tests/golden/make_mm_metrics.py)."""
+    import numpy as np
+    import os
+    import skeletondiffusion_b200 as sdb
+    from oracle import skeldiff_oracle as oc
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mm_metrics.npz"))
+    pred = torch.from_numpy(z["pred"])
+    counts = z["counts"].tolist()
+    flat = torch.from_numpy(z["mm_gt"])
+    mm_gt, o = [], 0
+    for c in counts:
+        mm_gt.append(flat[o:o + c])
+        o += c
+    a, f = sdb.multimodal_metrics(pred.to(cuda_device), [g.to(cuda_device) for g in mm_gt], scale=1.0)
+    assert torch.allclose(a.cpu(), oc.mmade(pred, mm_gt), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(f.cpu(), oc.mmfde(pred, mm_gt), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(a.cpu(), torch.from_numpy(z["mmade"]), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(f.cpu(), torch.from_numpy(z["mmfde"]), rtol=1e-5, atol=1e-6)
+    # frame window t0 / t and the pose-box scale
+    a2, f2 = sdb.multimodal_metrics(pred.to(cuda_device), [g.to(cuda_device) for g in mm_gt], scale=1.5, t0=2, t=9)
+    ref_a = 1.5 * oc.mmade(pred[:, :, 2:9], [g[:, 2:9] for g in mm_gt])
+    assert torch.allclose(a2.cpu(), ref_a, rtol=1e-5, atol=1e-6)
+    # twice the same call: bitwise
+    a3, f3 = sdb.multimodal_metrics(pred.to(cuda_device), [g.to(cuda_device) for g in mm_gt], scale=1.0)
+    assert torch.equal(a3, a) and torch.equal(f3, f)
+
+
+def test_long_term_prediction_matches_the_reference_function(cuda_device):
+    """long_term_prediction_best_every50 (src/eval_utils.py:44-67) around a deterministic stand-in predictor: the reference's own
+    function produced tests/golden/long_term.npz (make_long_term.py); ours runs the selection / feedback loop on the device."""
+    import numpy as np
+    import os
+    import skeletondiffusion_b200 as sdb
+    from skeletondiffusion_b200.testing import fake_predictor
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "long_term.npz"))
+    S, T, factor = int(z["S"]), int(z["T"]), float(z["factor"])
+    spec = sdb.get_skeleton("h36m")
+    predict = fake_predictor(int(z["seed"]), S, T)
+    d = cuda_device
+    tgt, pred, obs = sdb.long_term_prediction_best_every50(torch.from_numpy(z["data"]).to(d), torch.from_numpy(z["target"]).to(d), None, spec,
+                                                           num_samples=S, pred_length=T, long_term_factor=factor, predict_fn=predict)
+    assert tuple(pred.shape) == tuple(z["out_pred"].shape)
+    assert torch.allclose(pred.cpu(), torch.from_numpy(z["out_pred"]), atol=2e-6, rtol=1e-5)
+    assert torch.allclose(tgt.cpu(), torch.from_numpy(z["out_target"]), atol=1e-6)
+    assert torch.allclose(obs.cpu(), torch.from_numpy(z["out_obs"]), atol=1e-6)
+
+
+def test_best_sample_vs_oracle(cuda_device):
+    import skeletondiffusion_b200 as sdb
+    g = torch.Generator().manual_seed(4)
+    W, S, T, J = 9, 50, 13, 21
+    pred = torch.rand(W, S, T, J, 3, generator=g) * 2 - 1
+    target = torch.rand(W, T, J, 3, generator=g) * 2 - 1
+    ref_idx = torch.linalg.norm(pred - target.unsqueeze(1), dim=-1).mean(-1).mean(-1).min(dim=-1).indices      # src/metrics/utils.py:24
+    best, tail, idx = sdb.best_sample(pred.to(cuda_device), target.to(cuda_device), keep_frames=5, scale=1.5)
+    assert torch.equal(idx.cpu().long(), ref_idx)
+    ref_best = pred[torch.arange(W), ref_idx] * 1.5
+    assert torch.equal(best.cpu(), ref_best) and torch.equal(tail.cpu(), ref_best[:, -5:])
