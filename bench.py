@@ -35,8 +35,9 @@ def parse():
     ap.add_argument("--dataset", default="amass")
     ap.add_argument("--windows", type=int, default=512, help="observed windows per GPU per step (configs/config_eval/config.yaml:27)")
     ap.add_argument("--samples", type=int, default=50)
-    ap.add_argument("--precision", default=os.environ.get("SKELDIFF_PRECISION", "bf16x3"), choices=["fp32", "bf16", "bf16x3"],
-                    help="headline path: bf16x3 = fp32-grade tensor-core path (default), fp32 = FFMA2, bf16 = bf16 activations")
+    ap.add_argument("--precision", default=os.environ.get("SKELDIFF_PRECISION", "fp16x2"), choices=["fp32", "bf16", "bf16x3", "fp16x2"],
+                    help="headline path: fp16x2 (default) / bf16x3 = fp32-grade tensor-core paths (two fp16 / three bf16 operand planes), "
+                         "fp32 = FFMA2, bf16 = bf16 activations")
     ap.add_argument("--cpu-windows", type=int, default=64, help="windows of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--perturbed", action="store_true", help="dense non-identity graph-influence matrices (trained-model-like)")
@@ -241,7 +242,7 @@ def _timed_kernel(dev, fn, iters=10):
     return sum(ev[i].elapsed_time(ev[i + 1]) for i in range(iters)) / iters * 1e-3
 
 
-def kernel_rooflines(dev, spec, diff, peaks):
+def kernel_rooflines(dev, spec, diff, peaks, precision="fp16x2"):
     """The kernels that dominate each path, timed alone with CUDA events on torch's current stream (the stream the
     library launches on) at the full batch B = 25 600; every operand set is larger than the 126 MB L2.
     Algorithmic work per launch follows DESIGN.md section 4 / SURVEY section 8d."""
@@ -262,16 +263,29 @@ def kernel_rooflines(dev, spec, diff, peaks):
     hbm, tfl = peaks.get("hbm_gbs", 6650.0), peaks.get("bf16_tflops", 1590.0)
     flops = 2.0 * B * N * C * C                      # algorithmic fp32 FLOPs of one 192->192 graph-linear launch
     rl = {}
-    # (1) fp32-grade graph-linear on the tensor cores (bf16x3): 6 bf16 MMAs per fp32 product, fp32 activations in HBM.
-    # Floors for this launch: HBM 3 x 413 MB / peak = 0.19 ms; tensor 6 x 39.6 GFLOP / peak = 0.14 ms  =>  HBM-bound.
-    t = _timed_kernel(dev, lambda: plan.forward(x, scale_shift=ss, act=nv.ACT_TANH, residual=res, out=out, precision="bf16x3"))
+    # (1) fp32-grade graph-linear on the tensor cores, fp32 activations in HBM: fp16x2 = 3 fp16 MMAs per fp32 product (two operand
+    # planes), bf16x3 = 6 bf16 MMAs (three planes).  Floors for this launch: HBM 3 x 413 MB / peak = 0.19 ms; tensor 3 (6) x
+    # 39.6 GFLOP / peak = 0.07 (0.14) ms  =>  HBM-bound.  The layer with the Denoiser's commonest epilogue (tanh + residual).
     by3 = B * N * C * 4 * 3.0                        # read activations + read residual + write output, fp32
-    rl["glin_tc3"] = {"kernel": "glin_tc3_kernel (tcgen05, 3-plane split): graph-linear 192->192 +scale/shift +tanh +residual, fp32 I/O, B=25600",
-                      "bound": "hbm", "achieved": by3 / t / 1e9, "peak": hbm, "unit": "GB/s", "frac": by3 / t / 1e9 / hbm,
-                      "traffic": traffic.get("glin_tc3_kernel"), "ms": t * 1e3, "bytes_per_sample_layer": N * C * 4 * 3,
-                      "tensor": {"algorithmic_tflops": flops / t / 1e12, "issued_tflops_bf16": 6 * flops / t / 1e12,
-                                 "issued_frac_of_bf16_peak": 6 * flops / t / 1e12 / tfl, "peak_tflops": tfl},
-                      "flops_per_sample_layer": 2.0 * N * C * C, "peak_source": src}
+    for key, prec, mmas in (("glin_tc3", "fp16x2", 3), ("glin_tc3_bf16x3", "bf16x3", 6)):
+        t = _timed_kernel(dev, lambda: plan.forward(x, scale_shift=ss, act=nv.ACT_TANH, residual=res, out=out, precision=prec))
+        rl[key] = {"kernel": f"glin_tc3_kernel<PL={2 if mmas == 3 else 3}> (tcgen05, {prec} operand split): graph-linear 192->192 +scale/shift +tanh +residual, fp32 I/O, B=25600",
+                   "bound": "hbm", "achieved": by3 / t / 1e9, "peak": hbm, "unit": "GB/s", "frac": by3 / t / 1e9 / hbm,
+                   "traffic": traffic.get("glin_tc3_kernel_pl2" if mmas == 3 else "glin_tc3_kernel"), "ms": t * 1e3, "bytes_per_sample_layer": N * C * 4 * 3,
+                   "tensor": {"algorithmic_tflops": flops / t / 1e12, "issued_tflops_16bit": mmas * flops / t / 1e12,
+                              "issued_frac_of_bf16_peak": mmas * flops / t / 1e12 / tfl, "peak_tflops": tfl},
+                   "flops_per_sample_layer": 2.0 * N * C * C, "peak_source": src}
+    # the widest layer (to_qkv 192 -> 768, 20 % of a step): tensor-bound, reported against the dense 16-bit peak
+    att = diff.model.layers[0][1]                 # Residual(PreNorm(Attention))
+    lq = att.fn.fn.to_qkv.plan(fold_gain=att.fn.norm.g)
+    oq = torch.empty(B, N, 768, device=dev)
+    tq = _timed_kernel(dev, lambda: lq.forward(x, out=oq, precision=precision if precision in nv.FP32_GRADE_TC else "fp16x2"))
+    fq = 2.0 * B * N * C * 768
+    mm = 6 if precision == "bf16x3" else 3
+    rl["to_qkv"] = {"kernel": "glin_tc3_kernel: to_qkv 192->768 (activation-stationary schedule), fp32 I/O, B=25600", "bound": "tensor",
+                    "achieved": mm * fq / tq / 1e12, "peak": tfl, "unit": "TFLOP/s", "frac": mm * fq / tq / 1e12 / tfl, "traffic": None, "ms": tq * 1e3,
+                    "algorithmic_tflops": fq / tq / 1e12, "mmas_per_product": mm, "hbm_gbs": B * N * (C + 768) * 4.0 / tq / 1e9, "peak_source": src}
+    del oq
     # (2) exact-fp32 FFMA2 graph-linear
     t = _timed_kernel(dev, lambda: plan.forward(x, scale_shift=ss, act=nv.ACT_TANH, residual=res, out=out, precision="fp32"))
     rl["glin_ffma2"] = {"kernel": "glin_gemm_f2_kernel (FFMA2): same layer, exact fp32", "bound": "fp32 pipe (no tensor cores)",
@@ -436,7 +450,7 @@ def run_ours(args):
     # secondary precisions of the same pipeline (same inputs, same step definition), fewer steps
     others = {}
     eager = lambda: sdb.get_prediction(obs_dev, model, num_samples=S, pred_length=ph, diffusion_conditioning=True)
-    for prec in ("bf16", "fp32", "bf16x3"):
+    for prec in ("bf16", "fp32", "bf16x3", "fp16x2"):
         if prec == args.precision:
             continue
         diff.precision = prec
@@ -457,12 +471,15 @@ def run_ours(args):
         return
     motions = B * world * args.steps
     value, e2e = motions / t_res, motions / t_e2e
-    rl = kernel_rooflines(dev, spec, diff, peaks)
-    dominant = {"bf16x3": "glin_tc3", "fp32": "glin_ffma2", "bf16": "glin_tc_bf16"}[args.precision]
+    rl = kernel_rooflines(dev, spec, diff, peaks, args.precision)
+    dominant = {"fp16x2": "glin_tc3", "bf16x3": "glin_tc3_bf16x3", "fp32": "glin_ffma2", "bf16": "glin_tc_bf16"}[args.precision]
     dtype = {"fp32": "f32 (FFMA2, exact)", "bf16": "bf16 (tcgen05; stated tolerance, tests/test_gpu_tc.py)",
-             "bf16x3": "f32-grade: fp32 operands split into 3 bf16 planes on tcgen05, fp32 accumulate; <=1e-4 vs the reference (tests/test_gpu_tc.py)"}[args.precision]
+             "bf16x3": "f32-grade: fp32 operands split into 3 bf16 planes on tcgen05, fp32 accumulate; <=1e-4 vs the reference (tests/test_gpu_tc.py)",
+             "fp16x2": "f32-grade: fp32 operands split into 2 fp16 planes (22 significand bits) on tcgen05, fp32 accumulate; <=1e-4 vs the reference on every golden (tests/test_gpu_tc.py)"}[args.precision]
     if "bf16" in others:
         others["bf16"]["note"] = "bf16 activations between layers; latents within 5e-2, ADE/FDE/APD within 2 % of the fp32 reference (tests/test_gpu_tc.py)"
+    if "bf16x3" in others:
+        others["bf16x3"]["note"] = "three bf16 operand planes, six MMAs per product: exact operand split, any fp32 magnitude; same <=1e-4 gate"
     if "fp32" in others:
         others["fp32"]["note"] = "exact fp32 on the FFMA2 pipe, no tensor cores"
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,

@@ -39,6 +39,8 @@ extern "C" {
 #define SD_PREC_FP32 0      /* FFMA, fp32 operands and accumulation (parity gate <= 1e-4)            */
 #define SD_PREC_BF16 1      /* tcgen05 kind::f16, bf16 operands, fp32 accumulation in TMEM            */
 #define SD_PREC_BF16X3 2    /* tcgen05, operands split into 3 bf16 planes (fp32-grade products)       */
+#define SD_PREC_F16X2 3     /* as BF16X3 with operands split into 2 fp16 planes (hi + lo * 2^-11, 22 significand bits,
+                               three products instead of six); operands must stay below 65 504 in magnitude           */
 
 #define SD_ACT_NONE 0
 #define SD_ACT_TANH 1
@@ -78,6 +80,9 @@ int  sd_glin_create(int num_nodes, const int32_t* node_types_host, int n_types, 
                     const float* g_dev, sd_glin** out);
 /* optional bf16 weight planes [planes][n_types, out, in] for the tcgen05 paths (planes = 1 or 3) */
 int  sd_glin_set_bf16(sd_glin* L, const uint16_t* weight_bf16_dev, int planes);
+/* optional fp16 weight planes [2][n_types, out, in] = (fp16(w), fp16((w - fp16(w)) * 2^11)) for SD_PREC_F16X2
+ * (StaticGraphLinear weight, graph_structural.py:36); without them SD_PREC_F16X2 runs as SD_PREC_BF16X3 */
+int  sd_glin_set_f16x2(sd_glin* L, const uint16_t* weight_f16_dev);
 /* optional K-major fp32 copy [n_types, in, out] that enables the FFMA2 kernel (out % 96 == 0, in % 32 == 0) */
 int  sd_glin_set_kmajor(sd_glin* L, const float* weight_kmajor_dev);
 void sd_glin_destroy(sd_glin* L);
@@ -198,6 +203,8 @@ int  sd_gru_create(int num_nodes, const int32_t* node_types_host, int n_types, i
 /* Three bf16 planes of W_hh ([3][n_types][3H][H], w = p0 + p1 + p2 exactly) for the tcgen05 recurrent product
  * h W_hh^T (recurrent.py:339) of the bf16x3 / bf16 precisions.  Optional: without it the FFMA kernels are used. */
 int  sd_gru_set_bf16x3(sd_gru* g, const uint16_t* w_hh_planes_dev);
+/* Two fp16 planes of W_hh ([2][n_types][3H][H], as sd_glin_set_f16x2) for the recurrent product under SD_PREC_F16X2 (recurrent.py:339). */
+int  sd_gru_set_f16x2(sd_gru* g, const uint16_t* w_hh_f16_dev);
 int  sd_gru_set_fused(sd_gru* g, const float* w_ih_perm_dev, const float* w_hh_perm_dev,
                       const float* bias_ih_perm_dev, const float* bias_hh_perm_dev);
 void sd_gru_destroy(sd_gru* g);

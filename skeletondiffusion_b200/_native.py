@@ -19,7 +19,9 @@ _lib: Optional[C.CDLL] = None
 
 PREC_FP32, PREC_BF16, PREC_BF16X3 = 0, 1, 2
 ACT_NONE, ACT_TANH, ACT_TANH_TANH = 0, 1, 2
-PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16x3": PREC_BF16X3}
+PREC_F16X2 = 3
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16x3": PREC_BF16X3, "fp16x2": PREC_F16X2}
+FP32_GRADE_TC = ("bf16x3", "fp16x2")       # tensor-core precisions that meet the fp32 parity gate
 
 
 class NativeError(RuntimeError):
@@ -74,6 +76,8 @@ SIGNATURES = {
     "sd_gru_create": (_I, [_I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, C.POINTER(_P)]),
     "sd_gru_set_fused": (_I, [_P, _P, _P, _P, _P]),
     "sd_gru_set_bf16x3": (_I, [_P, _P]),
+    "sd_gru_set_f16x2": (_I, [_P, _P]),
+    "sd_glin_set_f16x2": (_I, [_P, _P]),
     "sd_gru_destroy": (None, [_P]),
     "sd_encode_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I]),
     "sd_encode": (_I, [_P, _P, _I, _P, _P, _I, _I, _I, _P, _I, _P, _I, _P]),

@@ -205,6 +205,16 @@ static int run_glin(const sd_glin* L, GlinCall c, int precision, cudaStream_t st
     return glin_forward_fp32(L->W, L->Wt, L->K, L->OUT, L->types, L->N, L->G, c, st);
 }
 
+// SD_PREC_F16X2 is SD_PREC_BF16X3 with the two-plane fp16 operand split: the entry points rewrite the precision and select the
+// split for the calls made on this thread while they run (nested entry points see SD_PREC_BF16X3 and leave the selection alone).
+struct SplitScope {
+    int prev; bool active;
+    explicit SplitScope(int& precision) : prev(tc_split_planes()), active(precision == SD_PREC_F16X2) {
+        if (active) { set_tc_split_planes(2); precision = SD_PREC_BF16X3; }
+    }
+    ~SplitScope() { if (active) set_tc_split_planes(prev); }
+};
+
 }  // namespace sd
 
 using namespace sd;
@@ -237,7 +247,7 @@ int sd_glin_create(int num_nodes, const int32_t* node_types_host, int n_types, i
         if (t < 0 || t >= n_types) { delete L; set_error("sd_glin_create: node type %d outside [0,%d)", t, n_types); return SD_ERR_INVALID; }
         L->types.t[n] = (unsigned char)t;
     }
-    L->W = weight_dev; L->Wt = nullptr; L->bias_node = bias_node_dev; L->G = g_dev; L->W_bf16 = nullptr; L->planes = 0;
+    L->W = weight_dev; L->Wt = nullptr; L->bias_node = bias_node_dev; L->G = g_dev; L->W_bf16 = nullptr; L->planes = 0; L->W_f16 = nullptr;
     L->G_host = nullptr;
     if (g_dev) {   // host copy: the per-sample mix kernels take G^ by value (constant bank)
         L->G_host = new (std::nothrow) float[(size_t)num_nodes * num_nodes];
@@ -252,6 +262,12 @@ int sd_glin_create(int num_nodes, const int32_t* node_types_host, int n_types, i
 int sd_glin_set_bf16(sd_glin* L, const uint16_t* weight_bf16_dev, int planes) {
     if (!L || (planes != 1 && planes != 3)) { set_error("sd_glin_set_bf16: invalid arguments"); return SD_ERR_INVALID; }
     L->W_bf16 = weight_bf16_dev; L->planes = planes;
+    return SD_OK;
+}
+
+int sd_glin_set_f16x2(sd_glin* L, const uint16_t* weight_f16_dev) {
+    if (!L || !weight_f16_dev) { set_error("sd_glin_set_f16x2: null argument"); return SD_ERR_INVALID; }
+    L->W_f16 = weight_f16_dev;
     return SD_OK;
 }
 
@@ -276,7 +292,9 @@ int sd_glin_forward(const sd_glin* L, const sd_glin_args* a, void* stream) {
     c.out = make_view_w(a->out);
     c.scratch = a->scratch_dev;
     c.B = a->batch;
-    return run_glin(L, c, a->precision, static_cast<cudaStream_t>(stream));
+    int precision = a->precision;
+    SplitScope split(precision);
+    return run_glin(L, c, precision, static_cast<cudaStream_t>(stream));
 }
 
 int sd_glin_forward_bf16(const sd_glin* L, const uint16_t* a_dev, const float* row_scale_dev, const float* ss_row_dev, int act,
@@ -373,6 +391,7 @@ int sd_denoiser_forward(const sd_denoiser* d, const sd_view* x, const sd_view* x
     if (!t_rows_dev && (t_row < 0 || t_row >= d->time_rows)) { set_error("sd_denoiser_forward: time row %d outside table of %d rows", t_row, d->time_rows); return SD_ERR_INVALID; }
     if ((d->cond_dim > 0) != (x_cond != nullptr && x_cond->ptr != nullptr)) { set_error("sd_denoiser_forward: x_cond presence does not match cond_dim=%d", d->cond_dim); return SD_ERR_INVALID; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SplitScope split(precision);
     if (precision == SD_PREC_BF16) return denoiser_forward_bf16(d, x, x_cond, t_rows_dev, t_row, out_dev, batch, workspace_dev, st);
     if (precision != SD_PREC_FP32 && precision != SD_PREC_BF16X3) { set_error("sd_denoiser_forward: precision %d not available", precision); return SD_ERR_UNSUPPORTED; }
     if (precision == SD_PREC_BF16X3 && t_rows_dev) precision = SD_PREC_FP32;   // per-sample times: FFMA kernels (both are fp32-grade)
@@ -547,6 +566,7 @@ int sd_sample_loop(const sd_diffusion* df, const sd_denoiser* dn, float* x_dev, 
     if (dn->time_rows < df->T) { set_error("sd_sample_loop: time table has %d rows, need %d", dn->time_rows, df->T); return SD_ERR_INVALID; }
     if (df->T > 1 && !sampling_noise_dev) { set_error("sd_sample_loop: sampling noise required"); return SD_ERR_INVALID; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SplitScope split(precision);
     const int B = batch, N = df->N, D = df->D, T = df->T;
     const size_t lat = (size_t)B * N * D;
     Arena ar(workspace_dev);
@@ -593,7 +613,7 @@ int sd_gru_create(int num_nodes, const int32_t* node_types_host, int n_types, in
     }
     g->W_ih = w_ih_dev; g->W_hh = w_hh_dev; g->bias_ih_seq = bias_ih_seq_dev; g->bias_hh_seq = bias_hh_seq_dev; g->gx_seq = gx_seq_dev;
     g->W_ih_perm = g->W_hh_perm = g->bias_ih_perm = g->bias_hh_perm = nullptr;
-    g->W_hh_planes = nullptr; g->gx_host = nullptr;
+    g->W_hh_planes = nullptr; g->W_hh_f16 = nullptr; g->gx_host = nullptr;
     if (gx_seq_dev) {   // host copy: the per-sample gate kernel takes gx_i by value (constant bank)
         const size_t n = (size_t)steps * num_nodes * num_nodes;
         g->gx_host = new (std::nothrow) float[n];
@@ -608,6 +628,12 @@ int sd_gru_create(int num_nodes, const int32_t* node_types_host, int n_types, in
 int sd_gru_set_bf16x3(sd_gru* g, const uint16_t* w_hh_planes_dev) {
     if (!g || !w_hh_planes_dev) { set_error("sd_gru_set_bf16x3: null argument"); return SD_ERR_INVALID; }
     g->W_hh_planes = w_hh_planes_dev;
+    return SD_OK;
+}
+
+int sd_gru_set_f16x2(sd_gru* g, const uint16_t* w_hh_f16_dev) {
+    if (!g || !w_hh_f16_dev) { set_error("sd_gru_set_f16x2: null argument"); return SD_ERR_INVALID; }
+    g->W_hh_f16 = w_hh_f16_dev;
     return SD_OK;
 }
 
@@ -639,7 +665,7 @@ static int gru_recurrent_product(const sd_gru* g, const View& h, float* hr, int 
         (reinterpret_cast<uintptr_t>(h.ptr) & 15u) == 0 && h.sb % 4 == 0 && h.sn % 4 == 0) {
         sd_glin rec;                                   // W_hh viewed as a graph-linear H -> 3H without bias or mix
         rec.N = N; rec.n_types = g->n_types; rec.K = H; rec.OUT = 3 * H; rec.types = g->types; rec.W = g->W_hh; rec.Wt = nullptr;
-        rec.bias_node = nullptr; rec.G = nullptr; rec.W_bf16 = g->W_hh_planes; rec.planes = 3; rec.G_host = nullptr;
+        rec.bias_node = nullptr; rec.G = nullptr; rec.W_bf16 = g->W_hh_planes; rec.planes = 3; rec.W_f16 = g->W_hh_f16; rec.G_host = nullptr;
         GlinCall c;
         c.a0 = h; c.a1 = null_view(); c.row_scale = nullptr; c.epi = no_epilogue(3 * H); c.scratch = nullptr; c.B = B;
         c.out = contiguous_view_w(hr, N, 3 * H);
@@ -661,6 +687,7 @@ int sd_encode(const sd_glin* initial_hidden, sd_gru* const* layers_host, int n_l
     if (windows == 0) return SD_OK;
     if (!initial_hidden || !layers_host || n_layers <= 0 || !fc || !obs_dev || !z_dev || !workspace_dev) { set_error("sd_encode: null argument"); return SD_ERR_INVALID; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SplitScope split(precision);
     const int W = windows, T = obs_len, N = initial_hidden->N, H = layers_host[0]->H;
     const size_t wn = (size_t)W * N;
     Arena ar(workspace_dev);
@@ -760,6 +787,7 @@ int sd_decode(const sd_glin* initial_hidden, const sd_gru* cell, const sd_glin* 
     if (!initial_hidden || !cell || !fc || !x_prev || !x_last || !latent_dev || !out_dev || !workspace_dev) { set_error("sd_decode: null argument"); return SD_ERR_INVALID; }
     if (cell->steps < ph) { set_error("sd_decode: GRU plan has %d steps, ph=%d", cell->steps, ph); return SD_ERR_INVALID; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SplitScope split(precision);
     const int B = batch, N = cell->N, H = cell->H, L = cell->IN - feat;
     if (L <= 0 || initial_hidden->K != cell->IN || fc->K != H || fc->OUT != feat) { set_error("sd_decode: layer shapes inconsistent"); return SD_ERR_INVALID; }
     const size_t bn = (size_t)B * N;

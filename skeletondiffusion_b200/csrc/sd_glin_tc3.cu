@@ -37,15 +37,20 @@ constexpr int T3_EPI_WARP0 = 8;     // warps 8-11: epilogue (warp % 4 = TMEM lan
 constexpr int T3_MMA_WARP = 12, T3_ALLOC_WARP = 12;   // warp 12: TMEM allocation, MMA issue (+ weight TMA in the weight-resident mode)
 constexpr int T3_WLOAD_WARP = 13;   // warp 13: weight-slot TMA ring of the activation-stationary mode
 constexpr int T3_THREADS = 448;     // 14 warps (register file is allocated as for 16: 128 registers per thread)
-constexpr int T3_MAX_STAGES = 4;
-constexpr int T3_STAGE_BYTES = 3 * T3_BM * 128;    // three plane tiles of 128 rows x 128 B
+constexpr int T3_MAX_STAGES = 8, T3_MAX_WSLOTS = 4;
+constexpr int T3_PLANE_BYTES = T3_BM * 128;         // one plane tile: 128 rows x 128 B (64 k of 16-bit operands)
+// PL = 3: three bf16 planes (exact split, any fp32 magnitude), six products.  PL = 2: two fp16 planes, x = hi + lo * 2^-11 with
+// hi = fp16(x), lo = fp16((x - hi) * 2^11): 22 significand bits, three products (hi hi | hi lo + lo hi, the latter scaled by
+// 2^-11 in the epilogue), |x| < 65 504 (larger operands become inf and the result NaN: loud, not silently wrong).
+__host__ __device__ constexpr int t3_stage_bytes(int planes) { return planes * T3_PLANE_BYTES; }
 
 struct T3Params {
     View a0, a1;
     int B, N, K, OUT, BN, NT, MT, KB, nstage, n_types, tmem_cols;
     int k_base;                 // first weight column of this launch (K-split of a two-segment layer)
     View pre;                   // fp32 partial product added before the epilogue (ptr null if none)
-    int a_stationary;           // 1: stage ring = the K/64 k-blocks of ONE m-tile, n-tiles looped inside the CTA, weights streamed
+    int a_stationary;           // 1: the stage ring holds the whole K of an m-tile, n-tiles looped inside the CTA, weights streamed
+    int wslots;                 // weight slots of the activation-stationary mode (2 .. T3_MAX_WSLOTS)
     NodeTypes types;
     const float* row_scale;
     const float* bias_node;
@@ -57,7 +62,7 @@ struct T3Params {
 struct __align__(8) T3Barriers {
     uint64_t full[T3_MAX_STAGES], empty[T3_MAX_STAGES];
     uint64_t w_full, w_empty;
-    uint64_t ws_full[2], ws_empty[2];       // weight slots (activation-stationary mode)
+    uint64_t ws_full[T3_MAX_WSLOTS], ws_empty[T3_MAX_WSLOTS];       // weight slots (activation-stationary mode)
     uint64_t acc_full[2], acc_empty[2];
     uint32_t tmem_base, pad;
 };
@@ -72,6 +77,14 @@ __device__ __forceinline__ void split3(float x, uint32_t& h, uint32_t& m, uint32
     const float r2 = r1 - __uint_as_float(m);
     l = __float_as_uint(r2) & 0xFFFF0000u;
 }
+// Two-plane fp16 split of a pair: hi = fp16(x) (one F2FP for both), lo = fp16((x - hi) * 2^11); x - hi is exact in fp32.
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn((a - hf.x) * 2048.0f, (b - hf.y) * 2048.0f);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 // Bulk L2 prefetch: brings `bytes` (multiple of 16) at p into L2 without occupying registers or shared memory.
 __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
@@ -82,7 +95,7 @@ __device__ __forceinline__ uint32_t pack_hi(uint32_t a, uint32_t b) { return __b
 // FAST: tanh through MUFU.EX2 + MUFU.RCP (tc::tanh_ex2, ~1e-7 absolute) instead of libdevice tanhf (SKELDIFF_ACCURATE_EPILOGUE=1)
 template <bool FAST> __device__ __forceinline__ float t3_tanh(float x) { return FAST ? tanh_ex2(x) : tanhf(x); }
 
-template <int ACT, bool HAS_RES, bool FAST>
+template <int ACT, bool HAS_RES, bool FAST, int PL>
 __global__ void __launch_bounds__(T3_THREADS, 1)
 glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -91,8 +104,9 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t w_block = (uint32_t)p.BN * 128u;                 // one (plane, k-block) weight tile
     uint8_t* w_smem = smem;                                        // resident: [plane][kb][BN x 128 B]; streamed: [slot][plane][BN x 128 B]
-    uint8_t* a_smem = w_smem + (size_t)3 * (p.a_stationary ? 2 : p.KB) * w_block;   // [stage][plane][128 x 128 B]
-    float* epi_mul = reinterpret_cast<float*>(a_smem + (size_t)p.nstage * T3_STAGE_BYTES);
+    constexpr int STAGE_BYTES = t3_stage_bytes(PL);
+    uint8_t* a_smem = w_smem + (size_t)PL * (p.a_stationary ? p.wslots : p.KB) * w_block;   // [stage][plane][128 x 128 B]
+    float* epi_mul = reinterpret_cast<float*>(a_smem + (size_t)p.nstage * STAGE_BYTES);
     float* epi_add = epi_mul + p.BN;
     float* epi_stage = epi_add + p.BN;                             // 4 warps x [32 rows][16 floats], swizzled
     T3Barriers* bars = reinterpret_cast<T3Barriers*>(epi_stage + 4 * 32 * 16);
@@ -103,7 +117,7 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
         for (int s = 0; s < p.nstage; ++s) { mbar_init(&bars->full[s], T3_PRODUCERS); mbar_init(&bars->empty[s], 1); }
         mbar_init(&bars->w_full, 1);
         mbar_init(&bars->w_empty, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(&bars->ws_full[s], 1); mbar_init(&bars->ws_empty[s], 1); }
+        for (int s = 0; s < T3_MAX_WSLOTS; ++s) { mbar_init(&bars->ws_full[s], 1); mbar_init(&bars->ws_empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&bars->acc_full[s], 1); mbar_init(&bars->acc_empty[s], 128); }
         fence_barrier_init();
     }
@@ -176,17 +190,25 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
             if (e_left <= 0) return;
             --e_left;
             mbar_wait(&bars->empty[stage], phase ^ 1);
-            uint8_t* st = a_smem + (size_t)stage * T3_STAGE_BYTES;
+            uint8_t* st = a_smem + (size_t)stage * STAGE_BYTES;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int r = row0 + 16 * i;
-                uint32_t h[4], m[4], l[4];
-                split3(v[i].x, h[0], m[0], l[0]); split3(v[i].y, h[1], m[1], l[1]);
-                split3(v[i].z, h[2], m[2], l[2]); split3(v[i].w, h[3], m[3], l[3]);
                 const uint32_t off = (uint32_t)r * 128u + ((chunk ^ (uint32_t)(r & 7)) << 4) + half;
-                *reinterpret_cast<uint2*>(st + off) = make_uint2(pack_hi(h[0], h[1]), pack_hi(h[2], h[3]));
-                *reinterpret_cast<uint2*>(st + T3_BM * 128 + off) = make_uint2(pack_hi(m[0], m[1]), pack_hi(m[2], m[3]));
-                *reinterpret_cast<uint2*>(st + 2 * T3_BM * 128 + off) = make_uint2(pack_hi(l[0], l[1]), pack_hi(l[2], l[3]));
+                if (PL == 3) {
+                    uint32_t h[4], m[4], l[4];
+                    split3(v[i].x, h[0], m[0], l[0]); split3(v[i].y, h[1], m[1], l[1]);
+                    split3(v[i].z, h[2], m[2], l[2]); split3(v[i].w, h[3], m[3], l[3]);
+                    *reinterpret_cast<uint2*>(st + off) = make_uint2(pack_hi(h[0], h[1]), pack_hi(h[2], h[3]));
+                    *reinterpret_cast<uint2*>(st + T3_PLANE_BYTES + off) = make_uint2(pack_hi(m[0], m[1]), pack_hi(m[2], m[3]));
+                    *reinterpret_cast<uint2*>(st + 2 * T3_PLANE_BYTES + off) = make_uint2(pack_hi(l[0], l[1]), pack_hi(l[2], l[3]));
+                } else {
+                    uint32_t h01, h23, l01, l23;
+                    split2(v[i].x, v[i].y, h01, l01);
+                    split2(v[i].z, v[i].w, h23, l23);
+                    *reinterpret_cast<uint2*>(st + off) = make_uint2(h01, h23);
+                    *reinterpret_cast<uint2*>(st + T3_PLANE_BYTES + off) = make_uint2(l01, l23);
+                }
             }
             fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
             mbar_arrive(&bars->full[stage]);
@@ -201,8 +223,8 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
     } else if (warp == T3_MMA_WARP) {
         // ================================================================ MMA issue (+ resident-weight TMA)
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(T3_BM, (uint32_t)p.BN);
-            int stage = 0; uint32_t phase = 0, acc = 0, acc_phase = 0, w_loads = 0, ws_cnt = 0;
+            const uint32_t idesc = PL == 3 ? umma_idesc_bf16(T3_BM, (uint32_t)p.BN) : umma_idesc_f16(T3_BM, (uint32_t)p.BN);
+            int stage = 0; uint32_t phase = 0, acc = 0, acc_phase = 0, w_loads = 0, ws_slot = 0, ws_phase = 0;
             long long cur_g = -1;
             for (long long it = item_lo; it < item_hi; ++it) {
                 const long long g = it / p.MT;
@@ -210,8 +232,8 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
                 if (!as_mode && g != cur_g) {
                     // the previous group's MMAs (w_empty phase w_loads-1) must have retired before the tile is overwritten
                     if (w_loads > 0) mbar_wait(&bars->w_empty, (w_loads - 1) & 1u);
-                    mbar_arrive_expect_tx(&bars->w_full, 3u * (uint32_t)p.KB * w_block);
-                    for (int pl = 0; pl < 3; ++pl)
+                    mbar_arrive_expect_tx(&bars->w_full, (uint32_t)PL * (uint32_t)p.KB * w_block);
+                    for (int pl = 0; pl < PL; ++pl)
                         for (int kb = 0; kb < p.KB; ++kb)
                             tma_load_3d(w_smem + (size_t)(pl * p.KB + kb) * w_block, &map_w, &bars->w_full, p.k_base + kb * T3_BK, my_nt * p.BN,
                                         pl * p.n_types + p.types.t[node]);
@@ -230,22 +252,21 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
                         const uint8_t* w_tile = w_smem;         // plane pw of this k-block at w_tile + pw * w_plane_stride
                         uint32_t w_plane_stride = (uint32_t)p.KB * w_block;
                         if (as_mode) {
-                            const uint32_t slot = ws_cnt & 1u;
-                            mbar_wait(&bars->ws_full[slot], (ws_cnt >> 1) & 1u);
-                            w_tile = w_smem + (size_t)slot * 3 * w_block; w_plane_stride = w_block;
+                            mbar_wait(&bars->ws_full[ws_slot], ws_phase);
+                            w_tile = w_smem + (size_t)ws_slot * PL * w_block; w_plane_stride = w_block;
                         } else {
                             w_tile = w_smem + (size_t)kb * w_block;
                         }
                         if (nt == nt_lo) mbar_wait(&bars->full[stage], phase);
                         tc_fence_after();
-                        const uint32_t a_base = smem_u32(a_smem + (size_t)stage * T3_STAGE_BYTES);
+                        const uint32_t a_base = smem_u32(a_smem + (size_t)stage * STAGE_BYTES);
                         uint32_t first_main = (kb == 0) ? 1u : 0u, first_corr = first_main;
 #pragma unroll
-                        for (int pa = 0; pa < 3; ++pa) {
+                        for (int pa = 0; pa < PL; ++pa) {
 #pragma unroll
-                            for (int pw = 0; pw < 3; ++pw) {
-                                if (pa + pw > 2) continue;
-                                const uint64_t adesc = umma_desc_sw128(a_base + (uint32_t)pa * T3_BM * 128);
+                            for (int pw = 0; pw < PL; ++pw) {
+                                if (pa + pw > PL - 1) continue;
+                                const uint64_t adesc = umma_desc_sw128(a_base + (uint32_t)pa * T3_PLANE_BYTES);
                                 const uint64_t bdesc = umma_desc_sw128(smem_u32(w_tile + (size_t)pw * w_plane_stride));
                                 const bool main_pair = (pa + pw == 0);
 #pragma unroll
@@ -257,7 +278,10 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
                                 }
                             }
                         }
-                        if (as_mode) { umma_commit(&bars->ws_empty[ws_cnt & 1u]); ++ws_cnt; }
+                        if (as_mode) {
+                            umma_commit(&bars->ws_empty[ws_slot]);
+                            if (++ws_slot == (uint32_t)p.wslots) { ws_slot = 0; ws_phase ^= 1u; }
+                        }
                         if (nt == nt_hi - 1) umma_commit(&bars->empty[stage]);     // the planes of this k-block are no longer needed
                         if (++stage == p.nstage) { stage = 0; phase ^= 1; }
                     }
@@ -272,17 +296,17 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
     } else if (warp == T3_WLOAD_WARP) {
         // ================================================================ weight-slot TMA ring (activation-stationary mode)
         if (as_mode && lane == 0) {
-            uint32_t cnt = 0;
+            uint32_t slot = 0, ph = 0;
             for (long long it = item_lo; it < item_hi; ++it) {
                 const int type = p.types.t[(int)(it / p.MT)];
                 for (int nt = 0; nt < p.NT; ++nt)
-                    for (int kb = 0; kb < p.KB; ++kb, ++cnt) {
-                        const uint32_t slot = cnt & 1u;
-                        mbar_wait(&bars->ws_empty[slot], ((cnt >> 1) & 1u) ^ 1u);
-                        mbar_arrive_expect_tx(&bars->ws_full[slot], 3u * w_block);
-                        for (int pl = 0; pl < 3; ++pl)
-                            tma_load_3d(w_smem + (size_t)(slot * 3 + pl) * w_block, &map_w, &bars->ws_full[slot], p.k_base + kb * T3_BK, nt * p.BN,
+                    for (int kb = 0; kb < p.KB; ++kb) {
+                        mbar_wait(&bars->ws_empty[slot], ph ^ 1u);
+                        mbar_arrive_expect_tx(&bars->ws_full[slot], (uint32_t)PL * w_block);
+                        for (int pl = 0; pl < PL; ++pl)
+                            tma_load_3d(w_smem + (size_t)(slot * PL + pl) * w_block, &map_w, &bars->ws_full[slot], p.k_base + kb * T3_BK, nt * p.BN,
                                         pl * p.n_types + type);
+                        if (++slot == (uint32_t)p.wslots) { slot = 0; ph ^= 1u; }
                     }
             }
         }
@@ -361,11 +385,12 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
                 __syncwarp();                                   // the previous chunk has been read out of the staging tile
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    float4 x;                                   // main + corr: one round-to-nearest add, then the row scale
-                    x.x = (__uint_as_float(v[4 * q + 0]) + __uint_as_float(vc[4 * q + 0])) * rs;
-                    x.y = (__uint_as_float(v[4 * q + 1]) + __uint_as_float(vc[4 * q + 1])) * rs;
-                    x.z = (__uint_as_float(v[4 * q + 2]) + __uint_as_float(vc[4 * q + 2])) * rs;
-                    x.w = (__uint_as_float(v[4 * q + 3]) + __uint_as_float(vc[4 * q + 3])) * rs;
+                    float4 x;                                   // main + corr: one round-to-nearest add (FMA for PL = 2), then the row scale
+                    constexpr float CS = PL == 3 ? 1.0f : 0.00048828125f;      // the lo planes carry a factor 2^11
+                    x.x = fmaf(__uint_as_float(vc[4 * q + 0]), CS, __uint_as_float(v[4 * q + 0])) * rs;
+                    x.y = fmaf(__uint_as_float(vc[4 * q + 1]), CS, __uint_as_float(v[4 * q + 1])) * rs;
+                    x.z = fmaf(__uint_as_float(vc[4 * q + 2]), CS, __uint_as_float(v[4 * q + 2])) * rs;
+                    x.w = fmaf(__uint_as_float(vc[4 * q + 3]), CS, __uint_as_float(v[4 * q + 3])) * rs;
                     *reinterpret_cast<float4*>(stg + lane * 16 + 4 * (q ^ ((lane >> 1) & 3))) = x;
                 }
                 __syncwarp();
@@ -413,36 +438,57 @@ typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
 
 static size_t t3_misc_smem(int bn) { return 2 * (size_t)bn * 4 + 4 * 32 * 16 * 4 + sizeof(T3Barriers) + 1024; }
 static int t3_kb(int K) { return (K + T3_BK - 1) / T3_BK; }      // the last k-block may be partly filled (zero planes)
-static size_t t3_fixed_smem(int K, int bn) { return (size_t)3 * t3_kb(K) * bn * 128 + t3_misc_smem(bn); }
-// activation-stationary mode: K/64 plane stages + two weight slots of 3 planes; widest n-tile that fits (>= 64 columns)
-static int t3_as_bn(int K, int OUT) {
+static size_t t3_fixed_smem(int K, int bn, int pl) { return (size_t)pl * t3_kb(K) * bn * 128 + t3_misc_smem(bn); }
+static int t3_env(const char* name, int dflt) { const char* e = getenv(name); return e && e[0] ? atoi(e) : dflt; }
+// activation-stationary mode: K/64 (+ extra) plane stages + the weight slots; widest n-tile that fits (>= 64 columns).
+// Three planes (48 KB stages): exactly K/64 stages and two slots fill the 227 KB.  Two planes (32 KB stages): the smaller stages
+// leave room for a third weight slot (the MMA thread waited on the two-slot ring) and for one stage of the NEXT m-tile.
+struct T3AsCfg { int bn, wslots, nstage; };
+static T3AsCfg t3_as_cfg(int K, int OUT, int pl) {
+    const int kb = t3_kb(K);
     const int cands[] = {128, 96, 64};
-    for (int bn : cands)
-        if (OUT % bn == 0 && OUT / bn >= 2 && (size_t)t3_kb(K) * T3_STAGE_BYTES + (size_t)2 * 3 * bn * 128 + t3_misc_smem(bn) <= 227 * 1024) return bn;
-    return 0;
+    static const int want_slots = t3_env("SKELDIFF_T3_WSLOTS", 3), want_extra = t3_env("SKELDIFF_T3_XSTAGES", 1);
+    for (int bn : cands) {
+        if (OUT % bn || OUT / bn < 2) continue;
+        auto fits = [&](int stages, int slots) {
+            return (size_t)stages * t3_stage_bytes(pl) + (size_t)slots * pl * bn * 128 + t3_misc_smem(bn) <= 227 * 1024;
+        };
+        if (pl == 3) { if (kb <= T3_MAX_STAGES && fits(kb, 2)) return {bn, 2, kb}; continue; }
+        for (int slots = want_slots > T3_MAX_WSLOTS ? T3_MAX_WSLOTS : want_slots; slots >= 2; --slots)
+            for (int extra = want_extra; extra >= 0; --extra)
+                if (kb + extra <= T3_MAX_STAGES && fits(kb + extra, slots)) return {bn, slots, kb + extra};
+    }
+    return {0, 0, 0};
 }
-static int t3_stages(int K, int bn) {
-    const size_t budget = 227 * 1024, fixed = t3_fixed_smem(K, bn);
-    if (fixed + 2 * (size_t)T3_STAGE_BYTES > budget) return 0;
-    const size_t n = (budget - fixed) / T3_STAGE_BYTES;
-    return (int)(n > T3_MAX_STAGES ? T3_MAX_STAGES : n);
+static int t3_stages(int K, int bn, int pl) {
+    const size_t budget = 227 * 1024, fixed = t3_fixed_smem(K, bn, pl);
+    if (fixed + 2 * (size_t)t3_stage_bytes(pl) > budget) return 0;
+    const size_t n = (budget - fixed) / t3_stage_bytes(pl);
+    return (int)(n > 4 ? 4 : n);
 }
-static int t3_pick_bn(int K, int OUT) {
+static int t3_pick_bn(int K, int OUT, int pl) {
     const int cands[] = {128, 96, 64, 32};    // 4 accumulators of BN fp32 columns must fit the 512 TMEM columns
-    for (int bn : cands) if (OUT % bn == 0 && t3_stages(K, bn) >= 2) return bn;
+    for (int bn : cands) if (OUT % bn == 0 && t3_stages(K, bn, pl) >= 2) return bn;
     return 0;
 }
 
 bool glin_tc3_supported(int K0, int K1, int OUT) {
     // segment widths: multiples of 4 (float4 granules); the weight rows (K bf16) must be 16-byte multiples for the TMA map
     if (K0 <= 0 || K0 % 4 || K1 % 4 || (K0 + K1) % 8) return false;
-    return t3_pick_bn(K0 + K1, OUT) != 0;
+    return t3_pick_bn(K0 + K1, OUT, 3) != 0;     // what fits three planes fits two
 }
 
-template <int ACT, bool HAS_RES, bool FAST = false>
+// operand split of the fp32-grade tensor-core path for the calls of this thread: 3 = bf16 planes, 2 = fp16 planes
+// (set by the C entry points from the precision argument: SD_PREC_BF16X3 / SD_PREC_F16X2)
+static thread_local int tl_split_planes = 3;
+int tc_split_planes() { return tl_split_planes; }
+void set_tc_split_planes(int planes) { tl_split_planes = planes == 2 ? 2 : 3; }
+
+template <int ACT, bool HAS_RES, int PL, bool FAST = false>
 static int t3_launch_t(const CUtensorMap& mw, const T3Params& p, int grid, size_t smem, cudaStream_t st) {
-    if (ACT != SD_ACT_NONE && !FAST && fast_epilogue()) return t3_launch_t<ACT, HAS_RES, ACT != SD_ACT_NONE>(mw, p, grid, smem, st);
-    auto kern = glin_tc3_kernel<ACT, HAS_RES, FAST>;
+    // the libdevice epilogue is kept for the three-plane kernel only (SKELDIFF_ACCURATE_EPILOGUE=1)
+    if (ACT != SD_ACT_NONE && !FAST && (PL == 2 || fast_epilogue())) return t3_launch_t<ACT, HAS_RES, PL, ACT != SD_ACT_NONE>(mw, p, grid, smem, st);
+    auto kern = glin_tc3_kernel<ACT, HAS_RES, FAST, PL>;
     static unsigned long long configured = 0;      // bit d: attribute set on device d (it is per device)
     if (int rc_attr = opt_in_smem(kern, (size_t)((227 * 1024)), configured)) return rc_attr;
     kern<<<grid, T3_THREADS, smem, st>>>(mw, p);
@@ -454,6 +500,7 @@ static int t3_launch_t(const CUtensorMap& mw, const T3Params& p, int grid, size_
 // one launch over the weight columns [k_base, k_base + K0 + K1) of the layer; `pre` (optional) is added before the epilogue
 static int t3_launch_one(const sd_glin* L, const GlinCall& c, const ViewW& out, bool apply_epilogue, int k_base, const View* pre, cudaStream_t st) {
     if (!L->W_bf16 || L->planes != 3) { set_error("bf16x3 path: 3-plane weights not set on this layer"); return SD_ERR_INVALID; }
+    const int PL = (tl_split_planes == 2 && L->W_f16) ? 2 : 3;
     const int K0 = c.a0.width, K1 = c.a1.ptr ? c.a1.width : 0;
     const int Kuse = K0 + K1;
     if (k_base < 0 || k_base % 8 || k_base + Kuse > L->K || !glin_tc3_supported(K0, K1, L->OUT)) { set_error("bf16x3 path: unsupported shape K=%d+%d (base %d of %d) OUT=%d", K0, K1, k_base, L->K, L->OUT); return SD_ERR_UNSUPPORTED; }
@@ -468,16 +515,17 @@ static int t3_launch_one(const sd_glin* L, const GlinCall& c, const ViewW& out, 
     }
     T3Params p;
     p.a0 = c.a0; p.a1 = c.a1; if (!c.a1.ptr) { p.a1 = c.a0; p.a1.width = 0; }
-    p.B = c.B; p.N = L->N; p.K = Kuse; p.OUT = L->OUT; p.BN = t3_pick_bn(Kuse, L->OUT); p.NT = L->OUT / p.BN;
-    p.MT = (c.B + T3_BM - 1) / T3_BM; p.KB = t3_kb(Kuse); p.nstage = t3_stages(Kuse, p.BN); p.n_types = L->n_types;
+    p.B = c.B; p.N = L->N; p.K = Kuse; p.OUT = L->OUT; p.BN = t3_pick_bn(Kuse, L->OUT, PL); p.NT = L->OUT / p.BN;
+    p.MT = (c.B + T3_BM - 1) / T3_BM; p.KB = t3_kb(Kuse); p.nstage = t3_stages(Kuse, p.BN, PL); p.n_types = L->n_types;
+    p.wslots = 2;
     p.k_base = k_base;
     if (pre) p.pre = *pre; else { p.pre.ptr = nullptr; p.pre.sb = p.pre.sn = 0; p.pre.rep = 1; p.pre.width = 0; }
     p.a_stationary = 0;
     {
         static int as_env = -1;              // SKELDIFF_TC3_AS=0 disables the activation-stationary schedule (A/B timing)
         if (as_env < 0) { const char* e = getenv("SKELDIFF_TC3_AS"); as_env = (e && e[0] == '0') ? 0 : 1; }
-        const int as_bn = as_env ? t3_as_bn(Kuse, L->OUT) : 0;
-        if (as_bn && p.NT >= 2 && p.KB <= T3_MAX_STAGES) { p.a_stationary = 1; p.BN = as_bn; p.NT = L->OUT / as_bn; p.nstage = p.KB; }
+        const T3AsCfg as = as_env ? t3_as_cfg(Kuse, L->OUT, PL) : T3AsCfg{0, 0, 0};
+        if (as.bn) { p.a_stationary = 1; p.BN = as.bn; p.NT = L->OUT / as.bn; p.nstage = as.nstage; p.wslots = as.wslots; }
     }
     p.tmem_cols = 4 * p.BN <= 32 ? 32 : (4 * p.BN <= 64 ? 64 : (4 * p.BN <= 128 ? 128 : (4 * p.BN <= 256 ? 256 : 512)));   // (main + corr) x 2 buffers
     p.types = L->types;
@@ -501,22 +549,26 @@ static int t3_launch_one(const sd_glin* L, const GlinCall& c, const ViewW& out, 
         enc = reinterpret_cast<EncodeTiledFn3>(fp);
     }
     CUtensorMap mw;
-    cuuint64_t dims[3] = {(cuuint64_t)L->K, (cuuint64_t)L->OUT, (cuuint64_t)(3 * L->n_types)};
+    cuuint64_t dims[3] = {(cuuint64_t)L->K, (cuuint64_t)L->OUT, (cuuint64_t)(PL * L->n_types)};
     cuuint64_t strides[2] = {(cuuint64_t)L->K * 2, (cuuint64_t)L->OUT * L->K * 2};
     cuuint32_t box[3] = {(cuuint32_t)T3_BK, (cuuint32_t)p.BN, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(&mw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<uint16_t*>(L->W_bf16), dims, strides, box, estr,
+    CUresult r = enc(&mw, PL == 3 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+                     const_cast<uint16_t*>(PL == 3 ? L->W_bf16 : L->W_f16), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (weights x3) failed: %d", (int)r); return SD_ERR_CUDA; }
-    const size_t smem = (p.a_stationary ? (size_t)2 * 3 * p.BN * 128 + t3_misc_smem(p.BN) : t3_fixed_smem(Kuse, p.BN)) + (size_t)p.nstage * T3_STAGE_BYTES;
+    const size_t smem = (p.a_stationary ? (size_t)p.wslots * PL * p.BN * 128 + t3_misc_smem(p.BN) : t3_fixed_smem(Kuse, p.BN, PL)) + (size_t)p.nstage * t3_stage_bytes(PL);
     const int sms = sm_count();
     long long gangs = p.a_stationary ? sms : sms / p.NT;
     if (gangs < 1) gangs = 1;
     if (gangs > (long long)p.N * p.MT) gangs = (long long)p.N * p.MT;
     const int grid = (int)(p.a_stationary ? gangs : gangs * p.NT);
-    if (act == SD_ACT_NONE) return has_res ? t3_launch_t<SD_ACT_NONE, true>(mw, p, grid, smem, st) : t3_launch_t<SD_ACT_NONE, false>(mw, p, grid, smem, st);
-    if (act == SD_ACT_TANH) return has_res ? t3_launch_t<SD_ACT_TANH, true>(mw, p, grid, smem, st) : t3_launch_t<SD_ACT_TANH, false>(mw, p, grid, smem, st);
-    if (act == SD_ACT_TANH_TANH) return has_res ? t3_launch_t<SD_ACT_TANH_TANH, true>(mw, p, grid, smem, st) : t3_launch_t<SD_ACT_TANH_TANH, false>(mw, p, grid, smem, st);
+#define T3_DISPATCH(PLN) \
+    if (act == SD_ACT_NONE) return has_res ? t3_launch_t<SD_ACT_NONE, true, PLN>(mw, p, grid, smem, st) : t3_launch_t<SD_ACT_NONE, false, PLN>(mw, p, grid, smem, st); \
+    if (act == SD_ACT_TANH) return has_res ? t3_launch_t<SD_ACT_TANH, true, PLN>(mw, p, grid, smem, st) : t3_launch_t<SD_ACT_TANH, false, PLN>(mw, p, grid, smem, st); \
+    if (act == SD_ACT_TANH_TANH) return has_res ? t3_launch_t<SD_ACT_TANH_TANH, true, PLN>(mw, p, grid, smem, st) : t3_launch_t<SD_ACT_TANH_TANH, false, PLN>(mw, p, grid, smem, st);
+    if (PL == 2) { T3_DISPATCH(2) } else { T3_DISPATCH(3) }
+#undef T3_DISPATCH
     set_error("bf16x3 path: unknown activation %d", act);
     return SD_ERR_INVALID;
 }
@@ -530,7 +582,8 @@ int glin_tc3_launch(const sd_glin* L, const GlinCall& c, const ViewW& out, bool 
     if (K0 + K1 != L->K) { set_error("bf16x3 path: operand widths %d+%d do not match the layer's K=%d", K0, K1, L->K); return SD_ERR_INVALID; }
     static int split_env = -1;               // SKELDIFF_TC3_KSPLIT=0 disables the K-split (A/B timing)
     if (split_env < 0) { const char* e = getenv("SKELDIFF_TC3_KSPLIT"); split_env = (e && e[0] == '0') ? 0 : 1; }
-    auto stationary_ok = [&](int K) { return t3_kb(K) <= T3_MAX_STAGES && t3_as_bn(K, L->OUT) != 0; };
+    const int PL = (tl_split_planes == 2 && L->W_f16) ? 2 : 3;
+    auto stationary_ok = [&](int K) { return t3_as_cfg(K, L->OUT, PL).bn != 0; };
     const bool split = split_env && K1 > 0 && apply_epilogue && c.scratch && c.scratch != out.ptr && !c.row_scale && !c.epi.residual.ptr &&
                        !stationary_ok(L->K) && stationary_ok(K0) && stationary_ok(K1);
     if (!split) return t3_launch_one(L, c, out, apply_epilogue, 0, nullptr, st);

@@ -12,6 +12,7 @@ struct sd_glin {
     const float* G;          // [N][N] or null (identity)
     const uint16_t* W_bf16;  // [planes][n_types][OUT][K] or null
     int planes;
+    const uint16_t* W_f16;   // [2][n_types][OUT][K] fp16 planes (hi, lo * 2^11) of the two-plane split, or null
     float* G_host;           // host copy of G (kernel-parameter constant bank of the per-sample mix kernels) or null
 };
 
@@ -25,6 +26,7 @@ struct sd_gru {
     const float* gx_seq;     // [steps][N][N] or null
     float* gx_host;          // host copy of gx_seq or null
     const uint16_t* W_hh_planes;   // [3][n_types][3H][H] bf16 planes of W_hh (tcgen05 recurrent product) or null
+    const uint16_t* W_hh_f16;      // [2][n_types][3H][H] fp16 planes (hi, lo * 2^11) or null
     // gate-interleaved copies for the fused FFMA2 GRU step (identity graph influence only); row c' = 96*blk + 32*g + u
     // holds original row g*H + 32*blk + u, so every 96-column GEMM block carries gates r|z|n of 32 units
     const float* W_ih_perm;  // [n_types][3H][IN]
@@ -82,6 +84,8 @@ int reverse_step_fp32(const sd_diffusion* d, const float* x_t, const float* x0, 
 int time_table_fp32(const float* times, int rows, int C, float theta, int time_dim, const float* w1, const float* b1,
                     const float* w3, const float* b3, const float* const* head_w, const float* const* head_b,
                     int n_heads, float* table, float* ws, cudaStream_t st);
+int tc_split_planes();                 // operand split of the fp32-grade tensor-core path for this thread: 3 (bf16) or 2 (fp16)
+void set_tc_split_planes(int planes);
 bool fast_epilogue();   // tanh / sigmoid of the fp32-grade tensor-core path through MUFU.EX2 + MUFU.RCP (default) or libdevice (SKELDIFF_ACCURATE_EPILOGUE=1)
 int fill_normal(float* out, long long count, uint64_t seed, uint64_t offset, cudaStream_t st);
 int motion_metrics_fp32(const float* pred, const float* target, int windows, int samples, int frames, int feat, float scale,

@@ -26,6 +26,14 @@ def _normalized_influence(G: torch.Tensor, learn_influence: bool) -> torch.Tenso
     return F.normalize(G, p=1.0, dim=1) if learn_influence else G
 
 
+def _f16x2_planes(w: torch.Tensor) -> torch.Tensor:
+    """[2, ...] fp16 planes of the two-plane operand split (SD_PREC_F16X2): w ~= hi + lo * 2^-11 with hi = fp16(w),
+    lo = fp16((w - hi) * 2^11); the residual is exact in fp32, so the pair carries 22 significand bits."""
+    hi = w.to(torch.float16)
+    lo = ((w - hi.float()) * 2048.0).to(torch.float16)
+    return torch.stack([hi, lo], 0).contiguous()
+
+
 def _is_identity(g: torch.Tensor) -> bool:
     return bool(torch.equal(g, torch.eye(g.shape[0], device=g.device, dtype=g.dtype)))
 
@@ -84,6 +92,8 @@ class GlinPlan:
         p2 = (r1 - p1.float()).to(torch.bfloat16)
         self.weight_bf16 = torch.stack([p0, p1, p2], 0).contiguous()
         nv.check(nv.load().sd_glin_set_bf16(self.handle, self.weight_bf16.data_ptr(), 3), "sd_glin_set_bf16")
+        self.weight_f16 = _f16x2_planes(self.weight)
+        nv.check(nv.load().sd_glin_set_f16x2(self.handle, self.weight_f16.data_ptr()), "sd_glin_set_f16x2")
 
     @classmethod
     def from_layer(cls, layer, fold_in: Optional[torch.Tensor] = None, key=None) -> "GlinPlan":
@@ -129,7 +139,7 @@ class GlinPlan:
         scratch = None
         if precision == "bf16":       # bf16 operand copy + fp32 raw product (see glin_forward_tc)
             scratch = Workspace.get(x.device, batch * self.N * (2 * self.in_features + 4 * self.out_features) + 1024, "glin")
-        elif not self.identity or (precision == "bf16x3" and x2 is not None):
+        elif not self.identity or (precision in nv.FP32_GRADE_TC and x2 is not None):
             # pre-mix product (non-identity G^) or the partial product of a K-split two-segment layer (bf16x3)
             scratch = Workspace.get(x.device, batch * self.N * self.out_features * 4, "glin")
         args.scratch_dev = nv.dptr(scratch)
@@ -295,6 +305,8 @@ class GruPlan:
         p2 = (r1 - p1.float()).to(torch.bfloat16)
         self.w_hh_planes = torch.stack([p0, p1, p2], 0).contiguous()
         nv.check(nv.load().sd_gru_set_bf16x3(self.handle, self.w_hh_planes.data_ptr()), "sd_gru_set_bf16x3")
+        self.w_hh_f16 = _f16x2_planes(self.w_hh)
+        nv.check(nv.load().sd_gru_set_f16x2(self.handle, self.w_hh_f16.data_ptr()), "sd_gru_set_f16x2")
         if self.identity and H % 32 == 0:
             # gate-interleaved copies for the fused FFMA2 GRU step: every 96-row block = gates r|z|n of 32 units
             blk = torch.arange(H // 32, device=dev).view(-1, 1, 1)

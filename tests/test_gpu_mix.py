@@ -21,7 +21,7 @@ def _layer(spec, kin, kout, bias, seed):
 
 
 @pytest.mark.parametrize("dataset", ["amass", "h36m", "freeman"])
-@pytest.mark.parametrize("kout,precision", [(192, "fp32"), (192, "bf16x3"), (96, "bf16x3"), (288, "fp32")])
+@pytest.mark.parametrize("kout,precision", [(192, "fp32"), (192, "bf16x3"), (96, "bf16x3"), (288, "fp32"), (192, "fp16x2"), (288, "fp16x2")])
 def test_dense_graph_linear_epilogue_vs_oracle(cuda_device, dataset, kout, precision):
     """Dense G^: raw products + sample_mix_kernel with bias, scale/shift, tanh and residual (64- and 32-column tasks)."""
     import skeletondiffusion_b200 as sdb
@@ -84,7 +84,7 @@ def test_attention_with_fused_qkv_mix_vs_oracle(cuda_device, dataset):
     att.load_state_dict(sd)
     x = torch.randn(77, N, 192, generator=torch.Generator().manual_seed(8))
     ref = oc._node_attention(sd, "fn.", x, 8, 32, nt, True)          # includes the residual (attention.py:16-17)
-    for precision in ("fp32", "bf16x3"):
+    for precision in ("fp32", "bf16x3", "fp16x2"):
         out = att.to(cuda_device)(x.to(cuda_device), precision=precision)
         assert G.rel_err(out.cpu(), ref) < FP32_TOL, precision
 
@@ -110,7 +110,7 @@ def test_denoiser_dense_influence_is_repeatable_at_full_size(cuda_device):
 
 
 @pytest.mark.parametrize("dataset", ["amass", "h36m", "freeman"])
-@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "fp16x2"])
 def test_decode_dense_influence_vs_oracle(cuda_device, dataset, precision):
     """Decoder with dense G / G_add / fc.G (gx_i changes every frame): tcgen05 recurrent product (bf16x3) or FFMA (fp32),
     gru_sample_kernel, gru_head_kernel; 25 frames so that the recurrence accumulates."""
@@ -142,7 +142,7 @@ def test_decode_dense_influence_vs_oracle(cuda_device, dataset, precision):
     assert G.rel_err(out2.cpu(), ref2) < FP32_TOL
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "fp16x2"])
 def test_encode_dense_influence_vs_oracle(cuda_device, precision):
     import skeletondiffusion_b200 as sdb
     from skeletondiffusion_b200.testing import synth_state_dict
