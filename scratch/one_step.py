@@ -10,7 +10,8 @@ if "--perturbed" in sys.argv:
     diff.load_state_dict(synth_state_dict(diff.state_dict(), seed=1, mode="perturbed", gain=2.5))
     ae.load_state_dict(synth_state_dict(ae.state_dict(), seed=2, mode="perturbed", gain=2.5))
 ae, diff = ae.to(dev).eval(), diff.to(dev).eval()
-diff.precision = "bf16x3"
+import os
+diff.precision = os.environ.get("SKELDIFF_PRECISION", "fp16x2")
 W, S, ph = 512, 50, spec.pred_length
 obs = (torch.randn(W, spec.obs_length, spec.num_nodes, 3, device=dev) * 0.3).clamp(-1, 1)
 for _ in range(2):

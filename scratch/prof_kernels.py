@@ -18,6 +18,8 @@ o16 = torch.empty_like(x16)
 ss = torch.zeros(1, 2 * C, device=dev)
 st = nv.stream_ptr(dev)
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
+import os
+PREC = os.environ.get("SKELDIFF_PRECISION", "fp16x2")
 x_t, x0, eps = (torch.randn(B, N, 96, device=dev) for _ in range(3))
 qkv_t = torch.randn(B, N, 768, device=dev)
 att = torch.empty(B, N, 256, device=dev)
@@ -28,15 +30,15 @@ def tc():
 
 
 def tc3():
-    plan.forward(x, scale_shift=ss, act=nv.ACT_TANH, residual=res, out=out, precision="bf16x3")
+    plan.forward(x, scale_shift=ss, act=nv.ACT_TANH, residual=res, out=out, precision=PREC)
 
 
 def tc3nr():
-    plan.forward(x, scale_shift=ss, act=nv.ACT_TANH, out=out, precision="bf16x3")
+    plan.forward(x, scale_shift=ss, act=nv.ACT_TANH, out=out, precision=PREC)
 
 
 def tc3raw():
-    plan.forward(x, out=out, precision="bf16x3")
+    plan.forward(x, out=out, precision=PREC)
 
 
 _qkv = {}
@@ -52,7 +54,7 @@ def qkv():
         _qkv["plan"] = mod.to_qkv.plan()
         _qkv["out"] = torch.empty(B, N, 768, device=dev)
         _qkv["rs"] = torch.rand(B, N, device=dev) + 0.5
-    _qkv["plan"].forward(x, row_scale=_qkv["rs"], out=_qkv["out"], precision="bf16x3")
+    _qkv["plan"].forward(x, row_scale=_qkv["rs"], out=_qkv["out"], precision=PREC)
 
 
 _to = {}
@@ -67,7 +69,7 @@ def toout():
             mod = mod.fn
         _to["plan"] = mod.to_out.plan()
         _to["x"] = torch.randn(B, N, 256, device=dev)
-    _to["plan"].forward(_to["x"], residual=res, out=out, precision="bf16x3")
+    _to["plan"].forward(_to["x"], residual=res, out=out, precision=PREC)
 
 
 def ffma():

@@ -36,13 +36,18 @@ constexpr int T3_PRODUCERS = 256;   // warps 0-7 (two per scheduler hide each ot
 constexpr int T3_EPI_WARP0 = 8;     // warps 8-11: epilogue (warp % 4 = TMEM lane quarter)
 constexpr int T3_MMA_WARP = 12, T3_ALLOC_WARP = 12;   // warp 12: TMEM allocation, MMA issue (+ weight TMA in the weight-resident mode)
 constexpr int T3_WLOAD_WARP = 13;   // warp 13: weight-slot TMA ring of the activation-stationary mode
-constexpr int T3_THREADS = 448;     // 14 warps (register file is allocated as for 16: 128 registers per thread)
+constexpr int T3_THREADS = 512;     // 16 warps = 4 warpgroups of 128 registers per thread at launch; warps 14-15 only take part in
+                                    // the register hand-over: warpgroup 3 (MMA / loader / idle) shrinks to T3_REGS_MISC per thread and
+                                    // the epilogue warpgroup grows to T3_REGS_EPI (setmaxnreg), which pays for a residual prefetch
+                                    // T3_RES_AHEAD chunks deep (one chunk in flight left the 4 warps waiting on L2 latency)
+constexpr int T3_REGS_MISC = 80, T3_REGS_EPI = 176, T3_RES_AHEAD = 3;
 constexpr int T3_MAX_STAGES = 8, T3_MAX_WSLOTS = 4;
 constexpr int T3_PLANE_BYTES = T3_BM * 128;         // one plane tile: 128 rows x 128 B (64 k of 16-bit operands)
 // PL = 3: three bf16 planes (exact split, any fp32 magnitude), six products.  PL = 2: two fp16 planes, x = hi + lo * 2^-11 with
 // hi = fp16(x), lo = fp16((x - hi) * 2^11): 22 significand bits, three products (hi hi | hi lo + lo hi, the latter scaled by
 // 2^-11 in the epilogue), |x| < 65 504 (larger operands become inf and the result NaN: loud, not silently wrong).
 __host__ __device__ constexpr int t3_stage_bytes(int planes) { return planes * T3_PLANE_BYTES; }
+__host__ __device__ constexpr int t3_chunk_cols(int planes) { return planes == 2 ? 32 : 16; }     // epilogue chunk width (columns)
 
 struct T3Params {
     View a0, a1;
@@ -108,8 +113,8 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
     uint8_t* a_smem = w_smem + (size_t)PL * (p.a_stationary ? p.wslots : p.KB) * w_block;   // [stage][plane][128 x 128 B]
     float* epi_mul = reinterpret_cast<float*>(a_smem + (size_t)p.nstage * STAGE_BYTES);
     float* epi_add = epi_mul + p.BN;
-    float* epi_stage = epi_add + p.BN;                             // 4 warps x [32 rows][16 floats], swizzled
-    T3Barriers* bars = reinterpret_cast<T3Barriers*>(epi_stage + 4 * 32 * 16);
+    float* epi_stage = epi_add + p.BN;                             // 4 warps x [32 rows][16 or 32 floats], swizzled
+    T3Barriers* bars = reinterpret_cast<T3Barriers*>(epi_stage + 4 * 32 * t3_chunk_cols(PL));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -220,7 +225,10 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
             fetch(vb); emit(va);
             fetch(va); emit(vb);
         }
-    } else if (warp == T3_MMA_WARP) {
+    } else if (warp >= 12) {
+      // warpgroup 3 (MMA issue, weight loader, two idle warps) hands registers over to the epilogue warpgroup
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(T3_REGS_MISC));
+      if (warp == T3_MMA_WARP) {
         // ================================================================ MMA issue (+ resident-weight TMA)
         if (lane == 0) {
             const uint32_t idesc = PL == 3 ? umma_idesc_bf16(T3_BM, (uint32_t)p.BN) : umma_idesc_f16(T3_BM, (uint32_t)p.BN);
@@ -293,7 +301,7 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
             }
         }
         __syncwarp();
-    } else if (warp == T3_WLOAD_WARP) {
+      } else if (warp == T3_WLOAD_WARP) {
         // ================================================================ weight-slot TMA ring (activation-stationary mode)
         if (as_mode && lane == 0) {
             uint32_t slot = 0, ph = 0;
@@ -311,12 +319,18 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
             }
         }
         __syncwarp();
-    } else if (warp >= T3_EPI_WARP0 && warp < T3_EPI_WARP0 + 4) {
+      }
+    } else {
         // ================================================================ epilogue (warps 8-11: warp % 4 = lane quarter)
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(T3_REGS_EPI));
         const int quarter = warp & 3;
         const int et = threadIdx.x - T3_EPI_WARP0 * 32;
-        float* stg = epi_stage + quarter * (32 * 16);
-        const int tr = lane >> 2, tc4 = lane & 3;
+        // Chunk geometry.  CW columns of the tile leave TMEM per step; LPR lanes cover the CW * 4 contiguous bytes of a row, so one
+        // LDG / STG.128 of the warp touches RPI rows and J instructions cover the 32 rows of the warp's lane quarter.
+        // CW = 32 (two planes: shared memory to spare): 128 contiguous bytes per row = whole L2 lines; CW = 16 (three planes): 64.
+        constexpr int CW = t3_chunk_cols(PL), LPR = CW / 4, RPI = 32 / LPR, J = 32 / RPI, AHEAD = (CW == 32) ? 2 : T3_RES_AHEAD;
+        float* stg = epi_stage + quarter * (32 * CW);
+        const int tr = lane / LPR, tcl = lane % LPR;
         uint32_t acc = 0, acc_phase = 0;
         long long cur_g = -1;
         for (long long it = item_lo; it < item_hi; ++it)
@@ -339,27 +353,30 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
             }
             // TMEM hands each lane one ROW of the tile; stored that way every LDG/STG.128 of a warp would touch 32
             // different rows (32 LSU wavefronts per instruction: in the second ncu capture the residual alone cost 140 us).
-            // Each 16-column chunk is therefore transposed through a 2 KB swizzled staging tile: afterwards four lanes
-            // cover the 64 contiguous bytes of a row and one instruction touches 8 rows.
+            // Each CW-column chunk is therefore transposed through a swizzled staging tile: afterwards LPR lanes cover the
+            // contiguous bytes of a row and one instruction touches RPI rows.
             const int b_own = mt * T3_BM + quarter * 32 + lane;
             const float rs = (b_own < p.B && p.row_scale) ? __ldg(p.row_scale + (long long)b_own * p.N + node) : 1.0f;
-            const int bT0 = mt * T3_BM + quarter * 32 + tr;                  // transposed mapping: rows bT0 + 8 j
+            const int bT0 = mt * T3_BM + quarter * 32 + tr;                  // transposed mapping: rows bT0 + RPI j
             const float* res_base = nullptr;
-            if (HAS_RES) res_base = p.residual.ptr + (long long)node * p.residual.sn + o0 + 4 * tc4;
-            float* out_base = p.out.ptr + (long long)node * p.out.sn + o0 + 4 * tc4;
-            long long res_off[4];
-            float4 rr[4];
+            if (HAS_RES) res_base = p.residual.ptr + (long long)node * p.residual.sn + o0 + 4 * tcl;
+            float* out_base = p.out.ptr + (long long)node * p.out.sn + o0 + 4 * tcl;
+            long long res_off[J];
+            float4 rr[AHEAD][J];                                // residual of the next AHEAD chunks (in flight)
             if (HAS_RES) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int bj = bT0 + 8 * j;
+                for (int j = 0; j < J; ++j) {
+                    const int bj = bT0 + RPI * j;
                     res_off[j] = (long long)(p.residual.rep == 1 ? bj : bj / p.residual.rep) * p.residual.sb;
-                    if (bj < p.B) rr[j] = __ldg(reinterpret_cast<const float4*>(res_base + res_off[j]));
                 }
+#pragma unroll
+                for (int a = 0; a < AHEAD; ++a)
+#pragma unroll
+                    for (int j = 0; j < J; ++j)
+                        if (bT0 + RPI * j < p.B && CW * a < p.BN) rr[a][j] = __ldg(reinterpret_cast<const float4*>(res_base + res_off[j] + CW * a));
             }
             if (HAS_RES && (nt + 1 < nt_hi || it + 1 < item_hi)) {
-                // The epilogue keeps one 2 KB residual chunk per warp in flight, far too little to cover DRAM latency;
-                // the NEXT pass's residual rows (one per thread) are pulled into L2 while this one is processed.
+                // The NEXT pass's residual rows (one per thread) are pulled into L2 while this one is processed.
                 const long long it2 = nt + 1 < nt_hi ? it : it + 1;
                 const int o2 = (nt + 1 < nt_hi ? nt + 1 : nt_lo) * p.BN;
                 const int b2 = (int)(it2 % p.MT) * T3_BM + quarter * 32 + lane, node2 = (int)(it2 / p.MT);
@@ -370,36 +387,44 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
             mbar_wait(&bars->acc_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 2u * (uint32_t)p.BN;
-            const float* pre_base = p.pre.ptr ? p.pre.ptr + (long long)node * p.pre.sn + o0 + 4 * tc4 : nullptr;
-            for (int c0 = 0; c0 < p.BN; c0 += 16) {
-                float4 pp[4];                                   // partial product of the first K segment (K-split layers)
+            const float* pre_base = p.pre.ptr ? p.pre.ptr + (long long)node * p.pre.sn + o0 + 4 * tcl : nullptr;
+            constexpr float CS = PL == 3 ? 1.0f : 0.00048828125f;        // the lo planes carry a factor 2^11
+            for (int c0 = 0; c0 < p.BN; c0 += CW) {
+                float4 pp[J];                                   // partial product of the first K segment (K-split layers)
                 if (pre_base) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        pp[j] = (bT0 + 8 * j < p.B) ? __ldg(reinterpret_cast<const float4*>(pre_base + (long long)(bT0 + 8 * j) * p.pre.sb + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int j = 0; j < J; ++j)
+                        pp[j] = (bT0 + RPI * j < p.B) ? __ldg(reinterpret_cast<const float4*>(pre_base + (long long)(bT0 + RPI * j) * p.pre.sb + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                uint32_t v[16], vc[16];
-                tmem_ld_32x16(t_row + (uint32_t)c0, v);
-                tmem_ld_32x16(t_row + (uint32_t)(p.BN + c0), vc);
-                tmem_ld_wait();
                 __syncwarp();                                   // the previous chunk has been read out of the staging tile
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float4 x;                                   // main + corr: one round-to-nearest add (FMA for PL = 2), then the row scale
-                    constexpr float CS = PL == 3 ? 1.0f : 0.00048828125f;      // the lo planes carry a factor 2^11
-                    x.x = fmaf(__uint_as_float(vc[4 * q + 0]), CS, __uint_as_float(v[4 * q + 0])) * rs;
-                    x.y = fmaf(__uint_as_float(vc[4 * q + 1]), CS, __uint_as_float(v[4 * q + 1])) * rs;
-                    x.z = fmaf(__uint_as_float(vc[4 * q + 2]), CS, __uint_as_float(v[4 * q + 2])) * rs;
-                    x.w = fmaf(__uint_as_float(vc[4 * q + 3]), CS, __uint_as_float(v[4 * q + 3])) * rs;
-                    *reinterpret_cast<float4*>(stg + lane * 16 + 4 * (q ^ ((lane >> 1) & 3))) = x;
+                for (int hf = 0; hf < CW / 16; ++hf) {              // 16 columns at a time: v + vc stay within 32 registers
+                    uint32_t v[16], vc[16];
+                    tmem_ld_32x16(t_row + (uint32_t)(c0 + 16 * hf), v);
+                    tmem_ld_32x16(t_row + (uint32_t)(p.BN + c0 + 16 * hf), vc);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float4 x;                               // main + corr: one round-to-nearest add (FMA for PL = 2), then the row scale
+                        x.x = fmaf(__uint_as_float(vc[4 * q + 0]), CS, __uint_as_float(v[4 * q + 0])) * rs;
+                        x.y = fmaf(__uint_as_float(vc[4 * q + 1]), CS, __uint_as_float(v[4 * q + 1])) * rs;
+                        x.z = fmaf(__uint_as_float(vc[4 * q + 2]), CS, __uint_as_float(v[4 * q + 2])) * rs;
+                        x.w = fmaf(__uint_as_float(vc[4 * q + 3]), CS, __uint_as_float(v[4 * q + 3])) * rs;
+                        // row = lane; the 16-byte chunk qq of the row is stored at position qq ^ f(row) (bank-conflict free both ways)
+                        const int qq = 4 * hf + q;
+                        const int sw = (CW == 32) ? (lane & 7) : ((lane >> 1) & 3);
+                        *reinterpret_cast<float4*>(stg + lane * CW + 4 * (qq ^ sw)) = x;
+                    }
                 }
                 __syncwarp();
-                const float4 m4 = *reinterpret_cast<const float4*>(epi_mul + c0 + 4 * tc4);
-                const float4 a4 = *reinterpret_cast<const float4*>(epi_add + c0 + 4 * tc4);
-                float4 o[4];
+                const float4 m4 = *reinterpret_cast<const float4*>(epi_mul + c0 + 4 * tcl);
+                const float4 a4 = *reinterpret_cast<const float4*>(epi_add + c0 + 4 * tcl);
+                float4 o[J];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float4 x = *reinterpret_cast<const float4*>(stg + (tr + 8 * j) * 16 + 4 * (tc4 ^ ((tr >> 1) & 3)));
+                for (int j = 0; j < J; ++j) {
+                    const int row = tr + RPI * j;
+                    const int sw = (CW == 32) ? (row & 7) : ((row >> 1) & 3);
+                    float4 x = *reinterpret_cast<const float4*>(stg + row * CW + 4 * (tcl ^ sw));
                     if (pre_base) { x.x += pp[j].x; x.y += pp[j].y; x.z += pp[j].z; x.w += pp[j].w; }
                     o[j].x = fmaf(x.x, m4.x, a4.x); o[j].y = fmaf(x.y, m4.y, a4.y);
                     o[j].z = fmaf(x.z, m4.z, a4.z); o[j].w = fmaf(x.w, m4.w, a4.w);
@@ -408,16 +433,23 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
                         o[j].x = t3_tanh<FAST>(t3_tanh<FAST>(o[j].x)); o[j].y = t3_tanh<FAST>(t3_tanh<FAST>(o[j].y));
                         o[j].z = t3_tanh<FAST>(t3_tanh<FAST>(o[j].z)); o[j].w = t3_tanh<FAST>(t3_tanh<FAST>(o[j].w));
                     }
-                    if (HAS_RES) { o[j].x += rr[j].x; o[j].y += rr[j].y; o[j].z += rr[j].z; o[j].w += rr[j].w; }
+                    if (HAS_RES) { o[j].x += rr[0][j].x; o[j].y += rr[0][j].y; o[j].z += rr[0][j].z; o[j].w += rr[0][j].w; }
                 }
-                if (HAS_RES && c0 + 16 < p.BN) {                // the next chunk's residual is in flight during this chunk's stores
+                if (HAS_RES) {                                  // rotate the ring, fetch the chunk AHEAD positions ahead
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (bT0 + 8 * j < p.B) rr[j] = __ldg(reinterpret_cast<const float4*>(res_base + res_off[j] + c0 + 16));
+                    for (int a = 0; a + 1 < AHEAD; ++a)
+#pragma unroll
+                        for (int j = 0; j < J; ++j) rr[a][j] = rr[a + 1][j];
+                    if (c0 + CW * AHEAD < p.BN) {
+#pragma unroll
+                        for (int j = 0; j < J; ++j)
+                            if (bT0 + RPI * j < p.B)
+                                rr[AHEAD - 1][j] = __ldg(reinterpret_cast<const float4*>(res_base + res_off[j] + c0 + CW * AHEAD));
+                    }
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int bj = bT0 + 8 * j;
+                for (int j = 0; j < J; ++j) {
+                    const int bj = bT0 + RPI * j;
                     if (bj < p.B) *reinterpret_cast<float4*>(out_base + (long long)bj * p.out.sb + c0) = o[j];
                 }
             }
@@ -436,22 +468,25 @@ typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static size_t t3_misc_smem(int bn) { return 2 * (size_t)bn * 4 + 4 * 32 * 16 * 4 + sizeof(T3Barriers) + 1024; }
+static size_t t3_misc_smem(int bn, int pl) { return 2 * (size_t)bn * 4 + 4 * 32 * t3_chunk_cols(pl) * 4 + sizeof(T3Barriers) + 1024; }
 static int t3_kb(int K) { return (K + T3_BK - 1) / T3_BK; }      // the last k-block may be partly filled (zero planes)
-static size_t t3_fixed_smem(int K, int bn, int pl) { return (size_t)pl * t3_kb(K) * bn * 128 + t3_misc_smem(bn); }
+static size_t t3_fixed_smem(int K, int bn, int pl) { return (size_t)pl * t3_kb(K) * bn * 128 + t3_misc_smem(bn, pl); }
 static int t3_env(const char* name, int dflt) { const char* e = getenv(name); return e && e[0] ? atoi(e) : dflt; }
 // activation-stationary mode: K/64 (+ extra) plane stages + the weight slots; widest n-tile that fits (>= 64 columns).
-// Three planes (48 KB stages): exactly K/64 stages and two slots fill the 227 KB.  Two planes (32 KB stages): the smaller stages
-// leave room for a third weight slot (the MMA thread waited on the two-slot ring) and for one stage of the NEXT m-tile.
+// Three planes (48 KB stages): exactly K/64 stages and two slots fill the 227 KB.  Two planes (32 KB stages): the same K/64
+// stages + two slots need 155 KB (K = 192) / 187 KB (K = 256).  A third or fourth weight slot and look-ahead stages of the next
+// m-tile were measured (SKELDIFF_T3_WSLOTS / SKELDIFF_T3_XSTAGES): every configuration above 196 KB -- the last shared-memory
+// carve-out step that leaves more than 28 KB of L1 to the producers' and the epilogue's global loads -- was 12 % SLOWER
+// (192 -> 192 bare: 235 vs 207 us, K = 256: 410 vs 374 us), so the smallest configuration is the default.
 struct T3AsCfg { int bn, wslots, nstage; };
 static T3AsCfg t3_as_cfg(int K, int OUT, int pl) {
     const int kb = t3_kb(K);
     const int cands[] = {128, 96, 64};
-    static const int want_slots = t3_env("SKELDIFF_T3_WSLOTS", 3), want_extra = t3_env("SKELDIFF_T3_XSTAGES", 1);
+    static const int want_slots = t3_env("SKELDIFF_T3_WSLOTS", 2), want_extra = t3_env("SKELDIFF_T3_XSTAGES", 0);
     for (int bn : cands) {
         if (OUT % bn || OUT / bn < 2) continue;
         auto fits = [&](int stages, int slots) {
-            return (size_t)stages * t3_stage_bytes(pl) + (size_t)slots * pl * bn * 128 + t3_misc_smem(bn) <= 227 * 1024;
+            return (size_t)stages * t3_stage_bytes(pl) + (size_t)slots * pl * bn * 128 + t3_misc_smem(bn, pl) <= 227 * 1024;
         };
         if (pl == 3) { if (kb <= T3_MAX_STAGES && fits(kb, 2)) return {bn, 2, kb}; continue; }
         for (int slots = want_slots > T3_MAX_WSLOTS ? T3_MAX_WSLOTS : want_slots; slots >= 2; --slots)
@@ -557,7 +592,7 @@ static int t3_launch_one(const sd_glin* L, const GlinCall& c, const ViewW& out, 
                      const_cast<uint16_t*>(PL == 3 ? L->W_bf16 : L->W_f16), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (weights x3) failed: %d", (int)r); return SD_ERR_CUDA; }
-    const size_t smem = (p.a_stationary ? (size_t)p.wslots * PL * p.BN * 128 + t3_misc_smem(p.BN) : t3_fixed_smem(Kuse, p.BN, PL)) + (size_t)p.nstage * t3_stage_bytes(PL);
+    const size_t smem = (p.a_stationary ? (size_t)p.wslots * PL * p.BN * 128 + t3_misc_smem(p.BN, PL) : t3_fixed_smem(Kuse, p.BN, PL)) + (size_t)p.nstage * t3_stage_bytes(PL);
     const int sms = sm_count();
     long long gangs = p.a_stationary ? sms : sms / p.NT;
     if (gangs < 1) gangs = 1;
