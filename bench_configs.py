@@ -235,9 +235,58 @@ def config5(sdb, dev, args):
     emit(config="5b: sampling loop (T x (Denoiser + fused step)), AMASS N=21, bf16x3, batch / timestep sweep", unit="ms per sample() call", loop=loop)
 
 
+def config_train(sdb, dev, args):
+    """Training step of the diffusion: TrainerDiffusion.loss with k = 50 samples per observation
+    (src/core/trainer.py:224-234, similarity in latent space) + backward, AMASS configuration, 64 observations per step.
+    Ours: all 3 200 loss values from the inference kernels, backward through the 64 selected rows only (training.SparseRowLoss).
+    Reference: its own p_losses + autograd on this GPU (oracle/_ref)."""
+    from skeletondiffusion_b200 import training
+    spec = sdb.get_skeleton("amass")
+    N, B, k = spec.num_nodes, 64, 50
+    g = torch.Generator().manual_seed(1)
+    x_start = torch.tanh(torch.randn(B, N, 96, generator=g)).to(dev)
+    x_cond = torch.tanh(torch.randn(B, N, 96, generator=g)).to(dev)
+    line = {"config": f"train: AMASS diffusion training step, {B} observations x k = {k} samples (best-of-k relaxation), loss + backward", "unit": "ms per step"}
+    _, diff = sdb.build_models(spec, "cpu")
+    with torch.enable_grad():
+        for prec in ("fp32", "fp16x2"):
+            diff = diff.to(dev).train()
+            diff.precision = prec
+
+            def step():
+                diff.zero_grad(set_to_none=True)
+                loss, w, _ = diff(x_start, x_cond=x_cond, n_train_samples=k)
+                sim, _ = training.ksimilarity_loss(loss, B)
+                (sim * w).mean().backward()
+
+            line[f"ours_{prec}_ms"] = cuda_time(dev, step, iters=10, warm=3) * 1e3
+
+        def step_dense():
+            diff.zero_grad(set_to_none=True)
+            loss, w, _ = diff(x_start.repeat_interleave(k, 0), x_cond=x_cond.repeat_interleave(k, 0), n_train_samples=1)
+            sim, _ = training.ksimilarity_loss(loss, B)
+            (sim * w[::k]).mean().backward()
+
+        line["ours_dense_autograd_all_rows_ms"] = cuda_time(dev, step_dense, iters=5, warm=2) * 1e3
+        from oracle import make_ref
+        if make_ref.add_to_path():
+            ae_r, diff_r, _ = bench.reference_models(spec, "amass", False, dev)
+            diff_r = diff_r.train()
+
+            def ref_step():
+                diff_r.zero_grad(set_to_none=True)
+                loss, w, _ = diff_r(x_start, x_cond=x_cond, n_train_samples=k)
+                idx = loss.detach().view(B, -1).min(-1).indices
+                (torch.gather(loss.view(B, -1), 1, idx.unsqueeze(1)).squeeze(-1) * w).mean().backward()
+
+            line["reference_gpu_eager_ms"] = cuda_time(dev, ref_step, iters=5, warm=2) * 1e3
+            line["reference"] = "unmodified reference p_losses + torch autograd (oracle/_ref), stock eager PyTorch on this GPU"
+    emit(**line)
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="1,2g,3,4,5")
+    ap.add_argument("--configs", default="1,2g,3,4,5,train")
     ap.add_argument("--windows", type=int, default=4096)
     args = ap.parse_args()
     import skeletondiffusion_b200 as sdb
@@ -257,6 +306,8 @@ def main():
             config4(sdb, dev, args, rank, world)
         if "5" in which and rank == 0:
             config5(sdb, dev, args)
+        if "train" in which and rank == 0:
+            config_train(sdb, dev, args)
     if torch.distributed.is_available() and torch.distributed.is_initialized():
         torch.distributed.destroy_process_group()
 

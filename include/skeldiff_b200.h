@@ -247,6 +247,37 @@ int  sd_multimodal_metrics(const float* pred_dev, const float* mm_gt_dev, const 
 int  sd_best_sample(const float* pred_dev, const float* target_dev, int windows, int samples, int frames, int joints, int keep_frames,
                     float scale, float* best_dev, float* tail_dev, int32_t* index_dev, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Training path: backward kernels behind forward() / p_losses with autograd (src/core/diffusion/base.py:262-307) and
+ * TrainerDiffusion.loss (src/core/trainer.py:224-234).  fp32; every reduction in a fixed order (repeatable gradients).
+ * ------------------------------------------------------------------------------------------------------------------- */
+/* out[b, m, :] = sum_n G[n, m] in[b, n, :]: the gradient of the node mix of GraphLinear.forward (graph_structural.py:41) */
+int  sd_node_mix_transposed(const float* g_dev, const float* in_dev, float* out_dev, int batch, int num_nodes, int width, void* stream);
+/* Parameter gradients of one StaticGraphLinear (graph_structural.py:30-43).  dym_dev = G^T dOut [B, N, out]; x_dev [B, N, in];
+ * y_raw_dev = x W[type]^T [B, N, out] (without bias), bias_types_dev [n_types, out] or null.  Each output is optional:
+ * dweight_dev [n_types, out, in], dbias_dev [n_types, out], dg_dev [N, N] (gradient with respect to the NORMALISED influence
+ * matrix); accumulate != 0 adds to the outputs.  scratch_dev: sd_glin_backward_scratch_bytes. */
+size_t sd_glin_backward_scratch_bytes(const sd_glin* L, int batch);
+int  sd_glin_backward_params(const sd_glin* L, const float* x_dev, const float* dym_dev, const float* dout_dev, const float* y_raw_dev,
+                             const float* bias_types_dev, float* dweight_dev, float* dbias_dev, float* dg_dev, float* scratch_dev,
+                             int batch, int accumulate, void* stream);
+/* Block (attention.py:66-76) without the projection: h = tanh(y (scale[t_b] + 1) + shift[t_b]); ss_table_dev [rows, 2 width]
+ * (scale | shift) indexed by t_dev [B], or null (h = tanh(y)).  Backward: dy and the per-sample sums dss_rows_dev [B, 2 width]. */
+int  sd_ss_tanh_forward(const float* y_dev, const float* ss_table_dev, const int32_t* t_dev, float* h_dev, int batch, int num_nodes, int width, void* stream);
+int  sd_ss_tanh_backward(const float* dh_dev, const float* h_dev, const float* y_dev, const float* ss_table_dev, const int32_t* t_dev,
+                         float* dy_dev, float* dss_rows_dev, int batch, int num_nodes, int width, void* stream);
+/* RMSNorm (attention.py:30-36): y = x / max(|x|, 1e-12) * g * sqrt(width); inv_dev [rows] keeps 1 / |x| for the backward, which
+ * writes dx and per-block partial sums of dg (dg_part_dev [sd_rmsnorm_backward_blocks(rows), width]; the caller adds the blocks). */
+int  sd_rmsnorm_forward(const float* x_dev, const float* g_dev, float* y_dev, float* inv_dev, int64_t rows, int width, void* stream);
+int  sd_rmsnorm_backward_blocks(int64_t rows);
+int  sd_rmsnorm_backward(const float* dy_dev, const float* x_dev, const float* inv_dev, const float* g_dev, float* dx_dev, float* dg_part_dev,
+                         int64_t rows, int width, void* stream);
+/* Backward of sd_node_attention (attention.py:121-136): dqkv [B, N, 3 heads dim_head] from qkv and dout [B, N, heads dim_head]. */
+int  sd_node_attention_backward(const float* qkv_dev, const float* dout_dev, float* dqkv_dev, int batch, int num_nodes, int heads, int dim_head, void* stream);
+/* Backward of sd_mahalanobis_loss (nonisotropic.py:176-190, 'l1'): dout = S[t]^T sign(S[t] (out - x0)) grad_loss / (N D). */
+int  sd_mahalanobis_loss_backward(const float* out_dev, const float* x0_dev, const int32_t* t_dev, const float* s_dev, const float* grad_loss_dev,
+                                  float* dout_dev, int batch, int num_nodes, int latent_dim, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,7 +12,7 @@ from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent / "csrc"
 LIB = CSRC / "libskeldiff_sm100a.so"
-SOURCES = ["sd_api.cu", "sd_mix.cu", "sd_glin_fp32.cu", "sd_glin_ffma2.cu", "sd_gru_ffma2.cu", "sd_elem_fp32.cu", "sd_attention.cu", "sd_glin_tc.cu", "sd_glin_tc3.cu", "sd_bf16.cu", "sd_metrics.cu"]
+SOURCES = ["sd_api.cu", "sd_mix.cu", "sd_glin_fp32.cu", "sd_glin_ffma2.cu", "sd_gru_ffma2.cu", "sd_elem_fp32.cu", "sd_attention.cu", "sd_glin_tc.cu", "sd_glin_tc3.cu", "sd_bf16.cu", "sd_metrics.cu", "sd_backward.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

@@ -73,6 +73,16 @@ SIGNATURES = {
     "sd_motion_metrics": (_I, [_P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P]),
     "sd_best_sample": (_I, [_P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P]),
     "sd_multimodal_metrics": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P]),
+    "sd_node_mix_transposed": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "sd_glin_backward_scratch_bytes": (C.c_size_t, [_P, _I]),
+    "sd_glin_backward_params": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "sd_ss_tanh_forward": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
+    "sd_ss_tanh_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "sd_rmsnorm_forward": (_I, [_P, _P, _P, _P, _I64, _I, _P]),
+    "sd_rmsnorm_backward_blocks": (_I, [_I64]),
+    "sd_rmsnorm_backward": (_I, [_P, _P, _P, _P, _P, _P, _I64, _I, _P]),
+    "sd_node_attention_backward": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "sd_mahalanobis_loss_backward": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "sd_gru_create": (_I, [_I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, C.POINTER(_P)]),
     "sd_gru_set_fused": (_I, [_P, _P, _P, _P, _P]),
     "sd_gru_set_bf16x3": (_I, [_P, _P]),

@@ -279,25 +279,40 @@ class NonisotropicGaussianDiffusion(LatentDiffusion):
         return out
 
     def p_losses(self, x_start, t, noise=None, x_cond=None, n_train_samples=1):
-        """Loss values of the training objective (base.py:262-300).  Forward only: the kernels carry no
-        autograd graph (backward kernels are the SURVEY §8f 'next' row)."""
+        """Training objective (base.py:262-300): returns (loss [B * k], loss_weight[t] [B], model_out).
+        Without autograd (torch.no_grad(), or a frozen Denoiser) the values come from the inference kernels alone.  With
+        autograd, k = 1 runs the differentiable Denoiser (training.py); k > 1 (TrainerDiffusion's best-of-k relaxation,
+        trainer.py:224-234) computes all B * k values with the inference kernels and differentiates only the rows that receive
+        a loss gradient (training.SparseRowLoss)."""
+        from . import training
         b = x_start.shape[0]
-        if n_train_samples > 1:
-            x_start = x_start.repeat_interleave(n_train_samples, dim=0)
-            t = t.repeat_interleave(n_train_samples, dim=0)
+        k = int(n_train_samples)
+        if k > 1:
+            x_start = x_start.repeat_interleave(k, dim=0)
+            t = t.repeat_interleave(k, dim=0)
         noise = noise if noise is not None else self.get_white_noise(x_start)
         x = self.q_sample(x_start=x_start, t=t, noise=noise)
-        model_out = self.feed_model(x, t, x_cond=x_cond)
         x_start = x_start.float().contiguous()
-        _, n, d = x_start.shape
-        loss = torch.empty(x_start.shape[0], device=x_start.device, dtype=torch.float32)
         if self.loss_reduction_type != "l1":
             raise NotImplementedError("loss_reduction_type 'mse'")
-        t32 = t.to(x_start.device, torch.int32).contiguous()
-        s_tab = self.mahalanobis_S_sqrt_recip.contiguous()
-        nv.check(nv.load().sd_mahalanobis_loss(model_out.data_ptr(), x_start.data_ptr(), t32.data_ptr(), s_tab.data_ptr(),
-                                               loss.data_ptr(), x_start.shape[0], n, d, nv.stream_ptr(x_start.device)),
-                 "sd_mahalanobis_loss")
+        params = list(self.model.parameters())
+        with_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        if with_grad and k == 1:
+            loss, model_out = training.diffusion_loss_train(self, x, x_start, t, x_cond)
+        else:
+            with torch.no_grad():
+                model_out = self.feed_model(x, t, x_cond=x_cond)
+                _, n, d = x_start.shape
+                loss = torch.empty(x_start.shape[0], device=x_start.device, dtype=torch.float32)
+                t32 = t.to(x_start.device, torch.int32).contiguous()
+                s_tab = self.mahalanobis_S_sqrt_recip.contiguous()
+                nv.check(nv.load().sd_mahalanobis_loss(model_out.data_ptr(), x_start.data_ptr(), t32.data_ptr(), s_tab.data_ptr(),
+                                                       loss.data_ptr(), x_start.shape[0], n, d, nv.stream_ptr(x_start.device)),
+                         "sd_mahalanobis_loss")
+            if with_grad:
+                xc = None if x_cond is None else x_cond.float().contiguous()
+                rep = 1 if xc is None else x_start.shape[0] // xc.shape[0]
+                loss = training.SparseRowLoss.apply(loss, self, x, x_start, t, xc, rep, *params)
         return loss, _extract(self.loss_weight, t.view(b, -1)[:, 0], loss.shape[0:1]), model_out
 
     # ------------------------------------------------------------------ reverse process

@@ -73,3 +73,11 @@ def fake_predictor(seed: int, num_samples: int, pred_length: int):
         return torch.tanh(m * a.to(obs.device).unsqueeze(0) + holder["b"].to(obs.device).unsqueeze(0)).contiguous()
 
     return predict
+
+
+def grad_probe_positions(name: str, numel: int, count: int = 64):
+    """Fixed pseudo-random positions at which the training goldens sample a large gradient tensor (tests/golden/make_training.py)."""
+    import zlib
+    import numpy as np
+    rs = np.random.RandomState(zlib.crc32(name.encode()) & 0x7FFFFFFF)
+    return torch.from_numpy(rs.randint(0, numel, size=count).astype("int64"))
