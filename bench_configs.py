@@ -58,7 +58,7 @@ def readme_diffusion(sdb, dev, precision):
 def config1(sdb, dev, args):
     """README configuration: the latency of one diffusion.sample(batch_size=4) call (10 steps, N = 16, depth 1)."""
     out = {}
-    for prec in ("bf16x3", "fp32"):
+    for prec in ("fp16x2", "fp32"):
         diff = readme_diffusion(sdb, dev, prec)
         for graph in (False, True):
             diff.use_cuda_graph = graph
@@ -120,7 +120,7 @@ def config2_gpu_reference(sdb, dev, args):
     # ours on the same window counts (eager launches and the whole-pipeline graph)
     ae_o, diff_o = bench.oracle_state(spec, False)
     model = (ae_o.to(dev).eval(), diff_o.to(dev).eval())
-    model[1].precision = "bf16x3"
+    model[1].precision = "fp16x2"
     ours = {}
     for w in (8, 64, 256, 512):
         obs = bench.synthetic_obs(spec, w, 123).to(dev)
@@ -129,11 +129,11 @@ def config2_gpu_reference(sdb, dev, args):
         ours[str(w)] = {"motions_per_s": w * 50 / t, "ms": t * 1e3}
         del g
     emit(config="2g: AMASS eval pipeline, the reference's own eager PyTorch code on this GPU next to ours (same GPU, same window counts)", unit="motions/s",
-         reference_gpu_eager=res, ours_graph_bf16x3=ours,
+         reference_gpu_eager=res, ours_graph_fp16x2=ours,
          note="reference = unmodified get_prediction from oracle/_ref, .to('cuda'), wall clock around torch.cuda.synchronize; best of 3")
 
 
-def pipeline_throughput(sdb, dev, spec, isotropic, windows, chunk, rank, world, precision="bf16x3", perturbed=False):
+def pipeline_throughput(sdb, dev, spec, isotropic, windows, chunk, rank, world, precision="fp16x2", perturbed=False):
     """Whole job of `windows` windows x 50 samples: this rank's shard in chunks of `chunk` windows through the graph."""
     import torch.distributed as dist
     from skeletondiffusion_b200.distributed import gather_window_metrics
@@ -184,7 +184,7 @@ def config3(sdb, dev, args, rank, world):
         res["isotropic" if iso else "nonisotropic"] = {"motions_per_s": 512 * world * 50 / t, "ms_per_512_windows": t * 1e3}
     if rank == 0:
         emit(config="3: AMASS shape, if_run_as_isotropic=True (U = I, Lambda = 1, Sigma = 0) through the same kernels, next to the nonisotropic run",
-             unit="motions/s", n_gpus=world, precision="bf16x3", **res)
+             unit="motions/s", n_gpus=world, precision="fp16x2", **res)
 
 
 def config4(sdb, dev, args, rank, world):
@@ -195,7 +195,7 @@ def config4(sdb, dev, args, rank, world):
             if rank == 0:
                 emit(config=f"4: {name} ({spec.num_nodes} nodes, obs {spec.obs_length} -> pred {spec.pred_length} frames), {args.windows} windows x 50 samples "
                             f"sharded over {world} GPU(s), chunks of 512 windows, ADE/FDE/APD per window + final NCCL gather inside the timed job",
-                     unit="motions/s", n_gpus=world, precision="bf16x3",
+                     unit="motions/s", n_gpus=world, precision="fp16x2",
                      weights="dense perturbed graph influence" if perturbed else "reference-style random init (identity graph influence)",
                      motions_per_s=args.windows * 50 / t, job_s=t, gathered_windows=int(gathered["ade"].numel()),
                      mean_ade=float(gathered["ade"].mean()), mean_apd=float(gathered["apd"].mean()))
@@ -222,7 +222,7 @@ def config5(sdb, dev, args):
     loop = {}
     for T, batches in ((10, (1, 16, 256, 4096, 25600, 65536)), (100, (1, 256, 4096)), (1000, (1, 256))):
         _, diff = sdb.build_models(spec, dev, diffusion_timesteps=T)
-        diff.precision = "bf16x3"
+        diff.precision = "fp16x2"
         for B in batches:
             cond = torch.tanh(torch.randn(B, N, D, device=dev))
             for graph in ((True, False) if B <= 256 else (False,)):
@@ -232,7 +232,7 @@ def config5(sdb, dev, args):
             del cond
         del diff
         torch.cuda.empty_cache()
-    emit(config="5b: sampling loop (T x (Denoiser + fused step)), AMASS N=21, bf16x3, batch / timestep sweep", unit="ms per sample() call", loop=loop)
+    emit(config="5b: sampling loop (T x (Denoiser + fused step)), AMASS N=21, fp16x2, batch / timestep sweep", unit="ms per sample() call", loop=loop)
 
 
 def config_train(sdb, dev, args):

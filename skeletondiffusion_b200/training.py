@@ -258,6 +258,9 @@ def denoiser_forward_train(model, x: torch.Tensor, t: torch.Tensor, x_cond: Opti
     nv.require_cuda(x, "x")
     t32 = t.to(x.device, torch.int32).contiguous()
     T = int(num_steps) if num_steps is not None else int(t32.max().item()) + 1
+    if x_cond is not None and x_cond.shape[0] != x.shape[0]:                     # conditioning shared by consecutive rows (samples of a window)
+        assert x.shape[0] % x_cond.shape[0] == 0, (x.shape, x_cond.shape)
+        x_cond = x_cond.repeat_interleave(x.shape[0] // x_cond.shape[0], dim=0)
     xin = torch.cat([x_cond, x], -1) if x_cond is not None else x               # generator.py:91-92
     h = graph_linear(model.init_lin, xin.float().contiguous(), precision)
     r = h
