@@ -88,13 +88,14 @@ fns = {"toout": toout, "qkv": qkv, "tc": tc, "tc3": tc3, "tc3nr": tc3nr, "tc3raw
 sel = list(fns) if which == "all" else which.split(",")
 for name in sel:
     fn = fns[name]
-    for _ in range(2):
+    for _ in range(int(os.environ.get("PROF_WARM", "2"))):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(5):
+    iters = int(os.environ.get("PROF_ITERS", "5"))
+    for _ in range(iters):
         fn()
     e1.record()
     torch.cuda.synchronize()
-    print(f"{name}: {e0.elapsed_time(e1) / 5 * 1e3:.1f} us")
+    print(f"{name}: {e0.elapsed_time(e1) / iters * 1e3:.1f} us")
