@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--perturbed", action="store_true", help="dense non-identity graph-influence matrices (trained-model-like)")
     ap.add_argument("--no-graph", action="store_true", help="eager kernel launches instead of the whole-pipeline CUDA graph")
     ap.add_argument("--no-general", action="store_true", help="skip the second headline (dense graph-influence weights)")
+    ap.add_argument("--no-others", action="store_true", help="skip the secondary precisions (shorter run, e.g. under ncu)")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference only: cpu = the reference arm (host cores); cuda = the same stock eager code on the GPU")
     return ap.parse_args()
@@ -366,7 +367,7 @@ def run_ours(args):
 
     def predict(o):
         if graphed is not None:
-            return graphed(o)
+            return graphed(o, window_offset=rank * W)       # noise indexed by the global window: independent of the rank count
         return sdb.get_prediction(o, model, num_samples=S, pred_length=ph, diffusion_conditioning=True)
 
     def step_resident():
@@ -451,7 +452,7 @@ def run_ours(args):
     others = {}
     eager = lambda: sdb.get_prediction(obs_dev, model, num_samples=S, pred_length=ph, diffusion_conditioning=True)
     for prec in ("bf16", "fp32", "bf16x3", "fp16x2"):
-        if prec == args.precision:
+        if prec == args.precision or args.no_others:
             continue
         diff.precision = prec
         for _ in range(2):

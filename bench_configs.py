@@ -156,7 +156,7 @@ def pipeline_throughput(sdb, dev, spec, isotropic, windows, chunk, rank, world, 
     def job():
         for c0 in range(0, mine, chunk):
             c1 = min(mine, c0 + chunk)
-            p = (g if c1 - c0 == chunk else g_tail)(obs[c0:c1])
+            p = (g if c1 - c0 == chunk else g_tail)(obs[c0:c1], window_offset=lo + c0)
             a, f, d = sdb.motion_metrics(tgt[c0:c1], p, scale=spec.pose_box_size)
             out["ade"][c0:c1], out["fde"][c0:c1], out["apd"][c0:c1] = a, f, d
 

@@ -9,6 +9,7 @@ from .autoencoder import AutoEncoder, Encoder, Decoder, StaticGraphGRU
 from .pipeline import (DiffusionManager, GraphedPrediction, best_sample, long_term_prediction_best_every50, get_prediction, get_diffusion_latent_codes, decode_latent_pred,
                        shard_windows, build_models)
 from .skeletons import get_skeleton, SkeletonSpec
+from .plan import invalidate_plans
 from .metrics import motion_metrics, multimodal_metrics, ade, fde, apd, mmade, mmfde
 
 __version__ = "0.1.0"

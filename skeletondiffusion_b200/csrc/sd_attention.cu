@@ -179,7 +179,11 @@ constexpr int AB_GROUPS = 1;                         // warp groups (group g tak
 constexpr int AB_COPY_WARP = AB_GROUPS * AB_HEADS;
 constexpr int AB_THREADS = (AB_COPY_WARP + 1) * 32;  // compute warps + 1 copy warp
 
-struct __align__(8) AbBarriers { uint64_t full[AB_STAGES], done[AB_STAGES]; };
+// MIX variant: 8 attention warps + 8 mix warps + the copy warp = 17 warps at 120 registers (no spills).  A version with 20 warps
+// and a setmaxnreg hand-over (copy / idle group 24, mix 88, attention 152) passed every small test and died with an illegal
+// instruction at B = 25 600 (the same kernel without the three setmaxnreg instructions is correct); not pursued, it is not needed.
+constexpr int AB_MIX_WARP0 = AB_HEADS, AB_MIX_WARPS = 8, AB_MIX_COPY_WARP = 16, AB_THREADS_MIX = 17 * 32;
+struct __align__(8) AbBarriers { uint64_t full[AB_STAGES], done[AB_STAGES], mixed[AB_STAGES]; };
 
 __device__ __forceinline__ void ab_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -212,9 +216,11 @@ __device__ __forceinline__ void ab_rotate8(float4 (&x)[8], int n) {
 // MIX: qkv holds the RAW per-node products of to_qkv and the graph-influence mix of that layer (graph_structural.py:41) is done
 // here, in place in shared memory, before the heads read the sample: thread = column (768 columns over 256 threads), the N
 // values of the column scaled by the RMSNorm row factor, N x N FFMAs with G^ in the constant bank (kernel parameter, see
-// sd_mix.cu), written back to the same N slots.  The mixed qkv tensor never exists in HBM.
+// sd_mix.cu), written back to the same N slots.  The mixed qkv tensor never exists in HBM.  The mix has its own eight warps and
+// runs one sample ahead of the heads (stages of the ring: loading / being mixed / being attended); a first version did mix and
+// attention back to back in the same eight warps (1.16 ms at B = 25 600 against 0.59 ms for the attention alone).
 template <int N, bool MIX>
-__global__ void __launch_bounds__(AB_THREADS, 1)
+__global__ void __launch_bounds__(MIX ? AB_THREADS_MIX : AB_THREADS, 1)
 node_attention_bulk_kernel(const float* __restrict__ qkv, float* __restrict__ out, int B, const __grid_constant__ MixMat<N> G,
                            const float* __restrict__ row_scale) {
     constexpr int ROW = 3 * AB_HEADS * AB_DH;                       // 768 floats per (sample, node) row: q | k | v, each [head][32]
@@ -225,12 +231,40 @@ node_attention_bulk_kernel(const float* __restrict__ qkv, float* __restrict__ ou
     AbBarriers* bars = reinterpret_cast<AbBarriers*>(in_buf + AB_STAGES * IN_FLOATS);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < AB_STAGES; ++s) { tc::mbar_init(&bars->full[s], 1); tc::mbar_init(&bars->done[s], AB_HEADS); }
+        for (int s = 0; s < AB_STAGES; ++s) {
+            tc::mbar_init(&bars->full[s], 1); tc::mbar_init(&bars->done[s], AB_HEADS); tc::mbar_init(&bars->mixed[s], AB_MIX_WARPS);
+        }
         tc::fence_barrier_init();
     }
     __syncthreads();
     const int my_samples = blockIdx.x < B ? (B - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    if (warp == AB_COPY_WARP) {
+    if (MIX && warp >= AB_MIX_WARP0 && warp < AB_MIX_COPY_WARP) {
+        // ------------------------------------------------------------ mix warps: sample k + 1 is mixed while the heads attend to k
+        // (thread = column, the N values of the column scaled by the RMSNorm row factor, N x N FFMAs with G^ in the constant
+        // bank, written back to the same N slots); mixed[stage] tells the head warps that the slab is ready.
+        const int mt = (int)threadIdx.x - AB_MIX_WARP0 * 32;
+        for (int k = 0; k < my_samples; ++k) {
+            const int stage = k % AB_STAGES;
+            tc::mbar_wait(&bars->full[stage], (uint32_t)(k / AB_STAGES) & 1u, 100000 + k);
+            float* slab = in_buf + stage * IN_FLOATS;
+            float rs[N];
+            const long long b = (long long)blockIdx.x + (long long)k * gridDim.x;
+#pragma unroll
+            for (int m = 0; m < N; ++m) rs[m] = row_scale ? __ldg(row_scale + b * N + m) : 1.0f;
+            for (int c = mt; c < ROW; c += AB_MIX_WARPS * 32) {
+                float in[N][1], acc[N][1];
+#pragma unroll
+                for (int m = 0; m < N; ++m) in[m][0] = slab[m * ROW + c] * rs[m];
+                mix_nodes<N, 1>(G, in, acc);
+#pragma unroll
+                for (int n2 = 0; n2 < N; ++n2) slab[n2 * ROW + c] = acc[n2][0];
+            }
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&bars->mixed[stage]);
+        }
+        return;
+    }
+    if (warp == (MIX ? AB_MIX_COPY_WARP : AB_COPY_WARP)) {
         // ------------------------------------------------------------ copy warp: bulk load per sample, bulk stores of its result
         // Head h writes its normalised output over ITS OWN q slice of the stage (a q row and an output row are both
         // [8 heads][32] floats), so the compute warps never synchronise with each other: each arrives on done[stage]
@@ -245,7 +279,7 @@ node_attention_bulk_kernel(const float* __restrict__ qkv, float* __restrict__ ou
             for (int k = 0; k < AB_STAGES && k < my_samples; ++k) load(k);
             for (int k = 0; k < my_samples; ++k) {
                 const int st = k % AB_STAGES;
-                tc::mbar_wait(&bars->done[st], (uint32_t)(k / AB_STAGES) & 1u);
+                tc::mbar_wait(&bars->done[st], (uint32_t)(k / AB_STAGES) & 1u, 300000 + k);
                 float* dst = out + ((long long)blockIdx.x + (long long)k * gridDim.x) * OUT_FLOATS;
                 const float* src = in_buf + st * IN_FLOATS;
 #pragma unroll 1
@@ -267,24 +301,7 @@ node_attention_bulk_kernel(const float* __restrict__ qkv, float* __restrict__ ou
     for (int i = 0; i < 8; ++i) rot[i] = 4 * ((i + n) & 7);
     for (int k = group; k < my_samples; k += AB_GROUPS) {
         const int stage = k % AB_STAGES;
-        tc::mbar_wait(&bars->full[stage], (uint32_t)(k / AB_STAGES) & 1u);
-        if (MIX) {
-            static_assert(AB_GROUPS == 1, "the in-place mix is shared by the eight head warps of one group");
-            float* slab = in_buf + stage * IN_FLOATS;
-            float rs[N];
-            const long long b = (long long)blockIdx.x + (long long)k * gridDim.x;
-#pragma unroll
-            for (int m = 0; m < N; ++m) rs[m] = row_scale ? __ldg(row_scale + b * N + m) : 1.0f;
-            for (int c = threadIdx.x; c < ROW; c += AB_HEADS * 32) {
-                float in[N][1], acc[N][1];
-#pragma unroll
-                for (int m = 0; m < N; ++m) in[m][0] = slab[m * ROW + c] * rs[m];
-                mix_nodes<N, 1>(G, in, acc);
-#pragma unroll
-                for (int n2 = 0; n2 < N; ++n2) slab[n2 * ROW + c] = acc[n2][0];
-            }
-            asm volatile("bar.sync 1, %0;" :: "n"(AB_HEADS * 32) : "memory");      // the eight head warps (not the copy warp)
-        }
+        tc::mbar_wait(MIX ? &bars->mixed[stage] : &bars->full[stage], (uint32_t)(k / AB_STAGES) & 1u, 200000 + k);
         float* blk = in_buf + stage * IN_FLOATS + h * AB_DH;
         if (active) {
             float2 q[16];
@@ -356,7 +373,7 @@ static int launch_attention_bulk(const float* qkv, float* out, int B, cudaStream
     if (int rc_attr = opt_in_smem(kern, (size_t)(smem), configured)) return rc_attr;
     const int sms = sm_count();
     const int grid = B < sms ? B : sms;                             // persistent: one CTA per SM, samples grid-strided
-    kern<<<grid, AB_THREADS, smem, st>>>(qkv, out, B, G, row_scale);
+    kern<<<grid, MIX ? AB_THREADS_MIX : AB_THREADS, smem, st>>>(qkv, out, B, G, row_scale);
     SD_LAUNCH_OK("node_attention_bulk_kernel");
     return SD_OK;
 }

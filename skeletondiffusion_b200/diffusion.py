@@ -146,20 +146,29 @@ class LatentDiffusion(nn.Module):
         nv.require_cuda(out, "noise")
         seed = (torch.initial_seed() + 0x9E3779B97F4A7C15 * (self._noise_calls + 1)) & 0xFFFFFFFFFFFFFFFF
         self._noise_calls += 1
-        nv.check(nv.load().sd_fill_normal(out.data_ptr(), out.numel(), seed, int(kwargs.get("offset", 0)),
+        nv.check(nv.load().sd_fill_normal(out.data_ptr(), out.numel(), seed, self._philox_offset(kwargs.get("offset", 0)),
                                           nv.stream_ptr(out.device)), "sd_fill_normal")
         return out
+
+    @staticmethod
+    def _philox_offset(element_offset: int) -> int:
+        """Element offset into the conceptual global noise tensor -> Philox counter offset (one counter per 4 elements)."""
+        element_offset = int(element_offset)
+        if element_offset % 4:
+            raise ValueError(f"noise offset must be a multiple of 4 elements, got {element_offset}")
+        return element_offset // 4
 
     get_white_noise = get_noise
     get_start_noise = get_noise
 
     def fill_noise_(self, out: torch.Tensor, offset: int = 0) -> torch.Tensor:
-        """White N(0, I) written into an existing contiguous fp32 CUDA tensor (same Philox stream as get_noise)."""
+        """White N(0, I) written into an existing contiguous fp32 CUDA tensor (same Philox stream as get_noise); `offset`: index of
+        out's first element in the conceptual global tensor (a shard of rows draws what the unsharded call would draw there)."""
         nv.require_cuda(out, "noise")
         assert out.dtype == torch.float32 and out.is_contiguous()
         seed = (torch.initial_seed() + 0x9E3779B97F4A7C15 * (self._noise_calls + 1)) & 0xFFFFFFFFFFFFFFFF
         self._noise_calls += 1
-        nv.check(nv.load().sd_fill_normal(out.data_ptr(), out.numel(), seed, int(offset), nv.stream_ptr(out.device)), "sd_fill_normal")
+        nv.check(nv.load().sd_fill_normal(out.data_ptr(), out.numel(), seed, self._philox_offset(offset), nv.stream_ptr(out.device)), "sd_fill_normal")
         return out
 
     # ------------------------------------------------------------------ network interface
@@ -357,7 +366,12 @@ class NonisotropicGaussianDiffusion(LatentDiffusion):
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 run()
-            entry = self._graphs[key] = dict(graph=graph, st=st)
+            # the entry keeps what the capture baked in alive (plans, workspace: their addresses cannot be reused while it
+            # lives) and entries captured for plans that have been replaced since are dropped
+            live = (dplan["handle"].value, mplan.handle.value)
+            for k_old in [k for k, e in self._graphs.items() if e["plans"] != live]:
+                del self._graphs[k_old]
+            entry = self._graphs[key] = dict(graph=graph, st=st, plans=live, refs=(dplan, mplan, ws))
         st = entry["st"]
         st["x"].copy_(img)
         if x_cond is not None:
@@ -395,7 +409,7 @@ class NonisotropicGaussianDiffusion(LatentDiffusion):
 
     @torch.no_grad()
     def p_sample_loop(self, shape, x_cond=None, start_noise=None, sampling_noise=None, return_sampling_noise=False,
-                      return_timages=False, clip_denoised=True, if_interpolate=False, **kwargs):
+                      return_timages=False, clip_denoised=True, if_interpolate=False, noise_row_offset: int = 0, **kwargs):
         """Full reverse process (base.py:343-390).  The common case runs as ONE native call
         (sd_sample_loop: T x (Denoiser kernels + fused step kernel), CUDA-graph capturable)."""
         device = self.betas.device
@@ -406,13 +420,15 @@ class NonisotropicGaussianDiffusion(LatentDiffusion):
             assert tuple(start_noise.shape) == tuple(shape), f"Shape mismatch: {start_noise.shape} != {shape}"
             img = start_noise.to(device, torch.float32)
         else:
-            img = self.get_start_noise(tuple(shape), device=device)
+            # noise_row_offset: global index of this call's first row (a rank's window shard x samples): the Philox stream
+            # is indexed by the global row, so the drawn noise does not depend on how the windows are sharded over ranks
+            img = self.get_start_noise(tuple(shape), device=device, offset=int(noise_row_offset) * N * D)
         noise0 = img.clone()
         if sampling_noise is not None:
             assert tuple(sampling_noise.shape) == (B, T - 1, N, D), f"Shape mismatch: {tuple(sampling_noise.shape)}"
             sampling_noise = sampling_noise.to(device, torch.float32).contiguous()
         elif T > 1:
-            sampling_noise = self.get_white_noise((B, T - 1, N, D), device=device)
+            sampling_noise = self.get_white_noise((B, T - 1, N, D), device=device, offset=int(noise_row_offset) * (T - 1) * N * D)
         if self.condition:
             assert x_cond is not None
         if return_timages or if_interpolate:                      # rarely used variants: per-step calls

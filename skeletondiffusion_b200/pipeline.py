@@ -181,8 +181,10 @@ class GraphedPrediction:
 
     @torch.no_grad()
     def __call__(self, obs: torch.Tensor, start_noise: Optional[torch.Tensor] = None, sampling_noise: Optional[torch.Tensor] = None,
-                 clone: bool = False) -> torch.Tensor:
-        """obs [W, T_obs, N, 3] -> predictions [W, S, pred_length, N, 3] (the graph's static output buffer unless clone=True)."""
+                 clone: bool = False, window_offset: int = 0) -> torch.Tensor:
+        """obs [W, T_obs, N, 3] -> predictions [W, S, pred_length, N, 3] (the graph's static output buffer unless clone=True).
+        window_offset: global index of obs[0] (a rank's shard / a chunk of a larger job): the noise of a window is drawn from the
+        Philox stream at its GLOBAL row index, so results do not depend on the number of ranks or the chunking."""
         ae, diff = self.model
         if obs.shape[0] != self.W:
             raise ValueError(f"graph was built for {self.W} windows, got {obs.shape[0]}")
@@ -194,12 +196,12 @@ class GraphedPrediction:
         if start_noise is not None:
             st["start"].copy_(start_noise)
         else:
-            diff.fill_noise_(st["start"])
+            diff.fill_noise_(st["start"], offset=int(window_offset) * self.S * st["start"][0].numel())
         if st["noise"].numel():
             if sampling_noise is not None:
                 st["noise"].copy_(sampling_noise)
             else:
-                diff.fill_noise_(st["noise"])
+                diff.fill_noise_(st["noise"], offset=int(window_offset) * self.S * st["noise"][0].numel())
         self._graph.replay()
         return st["pred"].clone() if clone else st["pred"]
 

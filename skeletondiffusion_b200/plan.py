@@ -14,11 +14,24 @@ import torch.nn.functional as F
 
 from . import _native as nv
 
-__all__ = ["params_key", "GlinPlan", "DenoiserPlan", "GruPlan", "Workspace"]
+__all__ = ["params_key", "invalidate_plans", "GlinPlan", "DenoiserPlan", "GruPlan", "Workspace"]
+
+
+_EPOCH = 0        # bumped by invalidate_plans(): part of every key
 
 
 def params_key(tensors: Sequence[Optional[torch.Tensor]]):
-    return tuple((t.data_ptr(), t._version, str(t.device)) if t is not None else None for t in tensors)
+    """Identity of a set of parameters: storage address, autograd version counter and device of each, plus the global epoch.
+    In-place writes through `.data` (`w.data.uniform_()`, `weight.data[1:] = ...`) do NOT bump the version counter: call
+    `invalidate_plans()` after such a write (optimizer steps, load_state_dict, .to() and `with torch.no_grad(): p.copy_()` do)."""
+    return (_EPOCH,) + tuple((t.data_ptr(), t._version, str(t.device)) if t is not None else None for t in tensors)
+
+
+def invalidate_plans() -> None:
+    """Force every packed plan (weight copies, operand planes, time tables, captured graphs keyed on them) to be rebuilt at its next
+    use.  Needed only after parameter writes that bypass autograd's version counter (`.data` assignments)."""
+    global _EPOCH
+    _EPOCH += 1
 
 
 def _normalized_influence(G: torch.Tensor, learn_influence: bool) -> torch.Tensor:

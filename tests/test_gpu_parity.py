@@ -332,3 +332,42 @@ def test_cuda_graph_sampling_matches_eager(cuda_device):
     assert len(diff._graphs) == 1
     assert torch.equal(g1, eager) and torch.equal(g2, eager2)
     assert G.rel_err(g1.cpu(), case["latents"]) < FP32_TOL
+
+
+def test_noise_does_not_depend_on_the_sharding(cuda_device):
+    """Philox noise is indexed by the GLOBAL row: a shard that passes its row / window offset draws exactly what the unsharded call
+    draws for those rows (results independent of the rank count), for sample() and for the captured pipeline graph."""
+    import skeletondiffusion_b200 as sdb
+    d = cuda_device
+    spec = sdb.get_skeleton("h36m")
+    ae, diff = sdb.build_models(spec, d, precision="fp16x2")
+    N, S, W = spec.num_nodes, 5, 6
+    cond = torch.tanh(torch.randn(W, N, 96, device=d))
+    torch.manual_seed(11); diff._noise_calls = 0
+    full, _ = diff.sample(batch_size=W * S, x_cond=cond)
+    torch.manual_seed(11); diff._noise_calls = 0
+    part, _ = diff.sample(batch_size=2 * S, x_cond=cond[4:6].contiguous(), noise_row_offset=4 * S)
+    assert torch.equal(part, full[4 * S:])
+    obs = (torch.randn(W, spec.obs_length, N, 3, device=d) * 0.3).clamp(-1, 1)
+    g_full, g_part = sdb.GraphedPrediction((ae, diff), W, S, 4, d), sdb.GraphedPrediction((ae, diff), 2, S, 4, d)
+    torch.manual_seed(5); diff._noise_calls = 0
+    p_full = g_full(obs, clone=True)
+    torch.manual_seed(5); diff._noise_calls = 0
+    p_part = g_part(obs[2:4].contiguous(), clone=True, window_offset=2)
+    assert torch.equal(p_part, p_full[2:4])
+
+
+def test_invalidate_plans_after_a_data_write(cuda_device):
+    """A `.data` write does not bump autograd's version counter, so the packed copies go stale until invalidate_plans()."""
+    import skeletondiffusion_b200 as sdb
+    d = cuda_device
+    spec = sdb.get_skeleton("h36m")
+    layer = sdb.StaticGraphLinear(96, 96, bias=True, num_nodes=spec.num_nodes, node_types=spec.nodes_type_id, learn_influence=True).to(d)
+    x = torch.randn(9, spec.num_nodes, 96, device=d)
+    a = layer(x, precision="fp16x2")
+    layer.weight.data.mul_(2.0)
+    sdb.invalidate_plans()
+    b = layer(x, precision="fp16x2")
+    assert not torch.allclose(a, b)
+    ref = oc.graph_linear({k: v.detach().cpu() for k, v in layer.state_dict().items()}, "", x.cpu(), spec.nodes_type_id, True)
+    assert G.rel_err(b.cpu(), ref) < 1e-5
