@@ -6,7 +6,7 @@ include/skeldiff_b200.h.  There is no CPU fallback."""
 from .diffusion import NonisotropicGaussianDiffusion, LatentDiffusion, get_cov_from_corr
 from .network import Denoiser, StaticGraphLinear, Attention, ResnetBlock, Residual, PreNorm, RMSNorm
 from .autoencoder import AutoEncoder, Encoder, Decoder, StaticGraphGRU
-from .pipeline import (DiffusionManager, GraphedPrediction, best_sample, long_term_prediction_best_every50, get_prediction, get_diffusion_latent_codes, decode_latent_pred,
+from .pipeline import (DiffusionManager, load_model_checkpoint, prepare_model, GraphedPrediction, best_sample, long_term_prediction_best_every50, get_prediction, get_diffusion_latent_codes, decode_latent_pred,
                        shard_windows, build_models)
 from .skeletons import get_skeleton, SkeletonSpec
 from .plan import invalidate_plans

@@ -18,6 +18,7 @@ from .network import Denoiser
 from .plan import params_key
 
 __all__ = ["DiffusionManager", "get_diffusion_latent_codes", "decode_latent_pred", "get_prediction", "GraphedPrediction",
+           "load_model_checkpoint", "prepare_model",
            "best_sample", "long_term_prediction_best_every50", "shard_windows", "build_models"]
 
 
@@ -52,6 +53,23 @@ class DiffusionManager:
         arch.pop("arch", None)
         return Denoiser(dim=latent_size, cond_dim=cond_dim, out_dim=latent_size, channels=num_nodes, num_nodes=num_nodes,
                         node_types=node_types, **arch)
+
+
+def load_model_checkpoint(load_path: str, map_location="cpu"):
+    """src/utils/load.py:11-17: the reference's checkpoints are `torch.save`d dicts whose 'model' entry is the state_dict
+    (the other entries - optimizer, epoch, EMA - belong to the trainer and are ignored here)."""
+    return torch.load(load_path, map_location=map_location, weights_only=False)
+
+
+def prepare_model(skeleton, autoencoder_checkpoint: str, diffusion_checkpoint: str, device="cuda", precision: str = "fp16x2", **manager_kwargs):
+    """prepare_autoencoder + prepare_model (src/eval_prepare_model.py:26-85) for the published layout: build the dataset-config
+    modules, `load_state_dict(checkpoint['model'])` with strict keys (the module and buffer names are the reference's, Appendix B
+    of the survey), move to `device`, eval().  Returns ((autoencoder, diffusion), device)."""
+    ae, diffusion = build_models(skeleton, "cpu", precision=precision, seed=None, **manager_kwargs)
+    ae.load_state_dict(load_model_checkpoint(autoencoder_checkpoint)["model"], strict=True)
+    diffusion.load_state_dict(load_model_checkpoint(diffusion_checkpoint)["model"], strict=True)
+    device = torch.device(device)
+    return (ae.to(device).eval(), diffusion.to(device).eval()), device
 
 
 def get_diffusion_latent_codes(obs, model, num_samples=50, **kwargs):

@@ -162,3 +162,30 @@ def test_metric_gather_world_size_2_gloo():
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_gloo_worker, args=(2, port, ret), nprocs=2, join=True)
     assert ret[0] and ret[1]
+
+
+def test_reference_checkpoint_files_load_unchanged(tmp_path):
+    """Checkpoint files written by the REFERENCE's own modules (torch.save({'model': state_dict, ...}), src/core/trainer.py /
+    src/utils/load.py:11-17) load into the drop-in modules with strict keys, and files written from OUR modules load into the
+    reference modules (oracle/_ref: present in the build container; skipped on a box without it)."""
+    import torch
+    from oracle import make_ref
+    if not make_ref.add_to_path():
+        pytest.skip("oracle/_ref absent")
+    import contextlib, io
+    import skeletondiffusion_b200 as sdb
+    import bench
+    spec = sdb.get_skeleton("h36m")
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref_ae, ref_diff, _ = bench._reference_models(spec, "h36m", False, torch.device("cpu"))
+    ae_path, diff_path = str(tmp_path / "checkpoint_100_val.pt"), str(tmp_path / "checkpoint_300_val.pt")
+    torch.save({"model": ref_ae.state_dict(), "epoch": 100, "optimizer": {}}, ae_path)
+    torch.save({"model": ref_diff.state_dict(), "epoch": 300, "ema": None}, diff_path)
+    (ae, diff), dev = sdb.prepare_model(spec, ae_path, diff_path, device="cpu")
+    for k, v in ref_diff.state_dict().items():
+        assert torch.equal(diff.state_dict()[k], v), k
+    for k, v in ref_ae.state_dict().items():
+        assert torch.equal(ae.state_dict()[k], v), k
+    # the other direction: a checkpoint written from our modules loads into the reference's, strict
+    torch.save({"model": diff.state_dict()}, diff_path)
+    ref_diff.load_state_dict(sdb.load_model_checkpoint(diff_path)["model"], strict=True)
