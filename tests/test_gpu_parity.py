@@ -371,3 +371,42 @@ def test_invalidate_plans_after_a_data_write(cuda_device):
     assert not torch.allclose(a, b)
     ref = oc.graph_linear({k: v.detach().cpu() for k, v in layer.state_dict().items()}, "", x.cpu(), spec.nodes_type_id, True)
     assert G.rel_err(b.cpu(), ref) < 1e-5
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16x2"])
+def test_amass_mano_reachability_pipeline_vs_oracle(cuda_device, precision):
+    """AMASS-MANO (configs/config_eval/dataset/amass-mano.yaml: 51 nodes, 43 node types) with covariance_matrix_type='reachability'
+    (kinematic/base.py:85-127), dense graph influence and typed weights: the whole pipeline against the oracle on the same injected
+    noise.  N = 51 has no specialised per-sample kernels: this is the generic path of every layer."""
+    import skeletondiffusion_b200 as sdb
+    from skeletondiffusion_b200.testing import synth_state_dict
+    d = cuda_device
+    spec = sdb.get_skeleton("amass-mano")
+    N, nt = spec.num_nodes, spec.nodes_type_id
+    torch.manual_seed(3)
+    ae = sdb.AutoEncoder(num_nodes=N, encoder_hidden_size=96, decoder_hidden_size=96, latent_size=96, node_types=nt, input_size=3,
+                         z_activation="tanh", enc_num_layers=spec.enc_num_layers, recurrent_arch_enc="StaticGraphGRU",
+                         recurrent_arch_decoder="StaticGraphGRU", output_size=3, if_consider_hip=False)
+    mgr = sdb.DiffusionManager(diffusion_type="NonisotropicGaussianDiffusion", skeleton=spec, covariance_matrix_type="reachability",
+                               reachability_matrix_degree_factor=0.5, reachability_matrix_stop_at="hips", num_nodes=N, node_types=nt,
+                               diffusion_conditioning=True, latent_size=96, diffusion_timesteps=10, diffusion_objective="pred_x0",
+                               beta_schedule="cosine", precision=precision,
+                               diffusion_arch=dict(depth=2, attn_heads=8, attn_dim_head=32, use_attention=True, self_condition=False,
+                                                   norm_type="none", learn_influence=True))
+    diff = mgr.get_diffusion()
+    tabs = {k: v.clone() for k, v in diff.state_dict().items() if not k.startswith("model.")}
+    diff_sd = synth_state_dict(diff.state_dict(), seed=61, mode="perturbed", gain=1.5)
+    diff_sd.update(tabs)
+    ae_sd = synth_state_dict(ae.state_dict(), seed=62, mode="perturbed", gain=1.5)
+    diff.load_state_dict(diff_sd); ae.load_state_dict(ae_sd)
+    W, S, ph = 3, 4, 5
+    g = torch.Generator().manual_seed(9)
+    obs = (torch.randn(W, spec.obs_length, N, 3, generator=g) * 0.3).clamp(-1, 1)
+    start = torch.randn(W * S, N, 96, generator=g)
+    noise = torch.randn(W * S, 9, N, 96, generator=g)
+    cfg = dict(dim=96, cond_dim=96, depth=2, attn_heads=8, attn_dim_head=32, node_types=nt, learn_influence=True, enc_num_layers=spec.enc_num_layers)
+    ref = oc.get_prediction(ae_sd, diff_sd, cfg, tabs, tabs["U"], obs, S, ph, start, noise)
+    ae, diff = ae.to(d).eval(), diff.to(d).eval()
+    pred = sdb.get_prediction(obs.to(d), (ae, diff), num_samples=S, pred_length=ph, diffusion_conditioning=True,
+                              sampler_kwargs=dict(start_noise=start.to(d), sampling_noise=noise.to(d)))
+    assert G.rel_err(pred.cpu(), ref) < FP32_TOL
