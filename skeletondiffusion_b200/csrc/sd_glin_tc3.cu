@@ -56,6 +56,7 @@ struct T3Params {
     View pre;                   // fp32 partial product added before the epilogue (ptr null if none)
     int a_stationary;           // 1: the stage ring holds the whole K of an m-tile, n-tiles looped inside the CTA, weights streamed
     int wslots;                 // weight slots of the activation-stationary mode (2 .. T3_MAX_WSLOTS)
+    int res_tma;                // 1: the residual tile rides a TMA ring (warp 14 -> two [128 rows][32 columns] boxes in shared memory)
     NodeTypes types;
     const float* row_scale;
     const float* bias_node;
@@ -69,6 +70,7 @@ struct __align__(8) T3Barriers {
     uint64_t w_full, w_empty;
     uint64_t ws_full[T3_MAX_WSLOTS], ws_empty[T3_MAX_WSLOTS];       // weight slots (activation-stationary mode)
     uint64_t acc_full[2], acc_empty[2];
+    uint64_t res_full[2], res_empty[2];     // residual chunk ring (res_tma)
     uint32_t tmem_base, pad;
 };
 
@@ -100,9 +102,9 @@ __device__ __forceinline__ uint32_t pack_hi(uint32_t a, uint32_t b) { return __b
 // FAST: tanh through MUFU.EX2 + MUFU.RCP (tc::tanh_ex2, ~1e-7 absolute) instead of libdevice tanhf (SKELDIFF_ACCURATE_EPILOGUE=1)
 template <bool FAST> __device__ __forceinline__ float t3_tanh(float x) { return FAST ? tanh_ex2(x) : tanhf(x); }
 
-template <int ACT, bool HAS_RES, bool FAST, int PL>
+template <int ACT, bool HAS_RES, bool FAST, int PL, bool RTMA>
 __global__ void __launch_bounds__(T3_THREADS, 1)
-glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
+glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_r, const T3Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment (SWIZZLE_128B atoms) by pointer arithmetic on the __shared__ array: rounding the address up through
     // uintptr_t made the compiler lose the address space and emit generic LD/ST for every shared-memory access of the kernel.
@@ -114,7 +116,9 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
     float* epi_mul = reinterpret_cast<float*>(a_smem + (size_t)p.nstage * STAGE_BYTES);
     float* epi_add = epi_mul + p.BN;
     float* epi_stage = epi_add + p.BN;                             // 4 warps x [32 rows][16 or 32 floats], swizzled
-    T3Barriers* bars = reinterpret_cast<T3Barriers*>(epi_stage + 4 * 32 * t3_chunk_cols(PL));
+    float* res_buf = epi_stage + 4 * 32 * t3_chunk_cols(PL);       // res_tma: 2 x [128 rows][32 floats]
+    constexpr int RES_BOX = T3_BM * 32;
+    T3Barriers* bars = reinterpret_cast<T3Barriers*>(res_buf + (RTMA ? 2 * RES_BOX : 0));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -124,6 +128,7 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
         mbar_init(&bars->w_empty, 1);
         for (int s = 0; s < T3_MAX_WSLOTS; ++s) { mbar_init(&bars->ws_full[s], 1); mbar_init(&bars->ws_empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&bars->acc_full[s], 1); mbar_init(&bars->acc_empty[s], 128); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&bars->res_full[s], 1); mbar_init(&bars->res_empty[s], 4); }
         fence_barrier_init();
     }
     if (warp == T3_ALLOC_WARP) tmem_alloc(&bars->tmem_base, (uint32_t)p.tmem_cols);
@@ -319,6 +324,25 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
             }
         }
         __syncwarp();
+      } else if (warp == T3_WLOAD_WARP + 1) {
+        // ================================================================ residual chunk ring (res_tma): one TMA box of
+        // [128 samples][32 columns] per epilogue chunk, in the epilogue's order, two boxes ahead of it.  The epilogue's own LDGs kept
+        // 16 KB per SM in flight at best; a box is 16 KB and two are outstanding while a third is being consumed.
+        if (RTMA && lane == 0) {
+            tma_prefetch_desc(&map_r);
+            uint32_t slot = 0, ph = 0;
+            for (long long it = item_lo; it < item_hi; ++it) {
+                const int node = (int)(it / p.MT), mt = (int)(it % p.MT);
+                for (int nt = nt_lo; nt < nt_hi; ++nt)
+                    for (int c0 = 0; c0 < p.BN; c0 += 32) {
+                        mbar_wait(&bars->res_empty[slot], ph ^ 1u);
+                        mbar_arrive_expect_tx(&bars->res_full[slot], (uint32_t)RES_BOX * 4u);
+                        tma_load_3d(res_buf + (size_t)slot * RES_BOX, &map_r, &bars->res_full[slot], nt * p.BN + c0, node, mt * T3_BM);
+                        if (++slot == 2) { slot = 0; ph ^= 1u; }
+                    }
+            }
+        }
+        __syncwarp();
       }
     } else {
         // ================================================================ epilogue (warps 8-11: warp % 4 = lane quarter)
@@ -332,6 +356,8 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
         float* stg = epi_stage + quarter * (32 * CW);
         const int tr = lane / LPR, tcl = lane % LPR;
         uint32_t acc = 0, acc_phase = 0;
+        uint32_t r_slot = 0, r_phase = 0;                          // residual chunk ring (res_tma)
+        constexpr bool res_tma = RTMA;
         long long cur_g = -1;
         for (long long it = item_lo; it < item_hi; ++it)
         for (int nt = nt_lo; nt < nt_hi; ++nt) {
@@ -363,7 +389,7 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
             float* out_base = p.out.ptr + (long long)node * p.out.sn + o0 + 4 * tcl;
             long long res_off[J];
             float4 rr[AHEAD][J];                                // residual of the next AHEAD chunks (in flight)
-            if (HAS_RES) {
+            if (HAS_RES && !res_tma) {
 #pragma unroll
                 for (int j = 0; j < J; ++j) {
                     const int bj = bT0 + RPI * j;
@@ -375,7 +401,7 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
                     for (int j = 0; j < J; ++j)
                         if (bT0 + RPI * j < p.B && CW * a < p.BN) rr[a][j] = __ldg(reinterpret_cast<const float4*>(res_base + res_off[j] + CW * a));
             }
-            if (HAS_RES && (nt + 1 < nt_hi || it + 1 < item_hi)) {
+            if (HAS_RES && !res_tma && (nt + 1 < nt_hi || it + 1 < item_hi)) {
                 // The NEXT pass's residual rows (one per thread) are pulled into L2 while this one is processed.
                 const long long it2 = nt + 1 < nt_hi ? it : it + 1;
                 const int o2 = (nt + 1 < nt_hi ? nt + 1 : nt_lo) * p.BN;
@@ -433,9 +459,22 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const T3Params p) {
                         o[j].x = t3_tanh<FAST>(t3_tanh<FAST>(o[j].x)); o[j].y = t3_tanh<FAST>(t3_tanh<FAST>(o[j].y));
                         o[j].z = t3_tanh<FAST>(t3_tanh<FAST>(o[j].z)); o[j].w = t3_tanh<FAST>(t3_tanh<FAST>(o[j].w));
                     }
-                    if (HAS_RES) { o[j].x += rr[0][j].x; o[j].y += rr[0][j].y; o[j].z += rr[0][j].z; o[j].w += rr[0][j].w; }
+                    if (HAS_RES && !res_tma) { o[j].x += rr[0][j].x; o[j].y += rr[0][j].y; o[j].z += rr[0][j].z; o[j].w += rr[0][j].w; }
                 }
-                if (HAS_RES) {                                  // rotate the ring, fetch the chunk AHEAD positions ahead
+                if (res_tma) {                                  // this chunk's residual box: rows of the warp's lane quarter
+                    mbar_wait(&bars->res_full[r_slot], r_phase);
+                    const float* rb = res_buf + (size_t)r_slot * RES_BOX + (quarter * 32 + tr) * 32 + 4 * tcl;
+#pragma unroll
+                    for (int j = 0; j < J; ++j) {
+                        const float4 r4 = *reinterpret_cast<const float4*>(rb + RPI * j * 32);
+                        o[j].x += r4.x; o[j].y += r4.y; o[j].z += r4.z; o[j].w += r4.w;
+                    }
+                    fence_proxy_async();                        // the reads above are ordered before the copy engine's refill
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->res_empty[r_slot]);
+                    if (++r_slot == 2) { r_slot = 0; r_phase ^= 1u; }
+                }
+                if (HAS_RES && !res_tma) {                      // rotate the ring, fetch the chunk AHEAD positions ahead
 #pragma unroll
                     for (int a = 0; a + 1 < AHEAD; ++a)
 #pragma unroll
@@ -519,14 +558,15 @@ static thread_local int tl_split_planes = 3;
 int tc_split_planes() { return tl_split_planes; }
 void set_tc_split_planes(int planes) { tl_split_planes = planes == 2 ? 2 : 3; }
 
-template <int ACT, bool HAS_RES, int PL, bool FAST = false>
-static int t3_launch_t(const CUtensorMap& mw, const T3Params& p, int grid, size_t smem, cudaStream_t st) {
+template <int ACT, bool HAS_RES, int PL, bool FAST = false, bool RTMA = false>
+static int t3_launch_t(const CUtensorMap& mw, const CUtensorMap& mr, const T3Params& p, int grid, size_t smem, cudaStream_t st) {
     // the libdevice epilogue is kept for the three-plane kernel only (SKELDIFF_ACCURATE_EPILOGUE=1)
-    if (ACT != SD_ACT_NONE && !FAST && (PL == 2 || fast_epilogue())) return t3_launch_t<ACT, HAS_RES, PL, ACT != SD_ACT_NONE>(mw, p, grid, smem, st);
-    auto kern = glin_tc3_kernel<ACT, HAS_RES, FAST, PL>;
+    if (ACT != SD_ACT_NONE && !FAST && (PL == 2 || fast_epilogue())) return t3_launch_t<ACT, HAS_RES, PL, ACT != SD_ACT_NONE, RTMA>(mw, mr, p, grid, smem, st);
+    if (HAS_RES && PL == 2 && !RTMA && p.res_tma) return t3_launch_t<ACT, HAS_RES, PL, FAST, HAS_RES && PL == 2>(mw, mr, p, grid, smem, st);
+    auto kern = glin_tc3_kernel<ACT, HAS_RES, FAST, PL, RTMA>;
     static unsigned long long configured = 0;      // bit d: attribute set on device d (it is per device)
     if (int rc_attr = opt_in_smem(kern, (size_t)((227 * 1024)), configured)) return rc_attr;
-    kern<<<grid, T3_THREADS, smem, st>>>(mw, p);
+    kern<<<grid, T3_THREADS, smem, st>>>(mw, mr, p);
     SD_LAUNCH_OK("glin_tc3_kernel");
     return SD_OK;
 }
@@ -592,16 +632,38 @@ static int t3_launch_one(const sd_glin* L, const GlinCall& c, const ViewW& out, 
                      const_cast<uint16_t*>(PL == 3 ? L->W_bf16 : L->W_f16), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (weights x3) failed: %d", (int)r); return SD_ERR_CUDA; }
-    const size_t smem = (p.a_stationary ? (size_t)p.wslots * PL * p.BN * 128 + t3_misc_smem(p.BN, PL) : t3_fixed_smem(Kuse, p.BN, PL)) + (size_t)p.nstage * t3_stage_bytes(PL);
+    size_t smem = (p.a_stationary ? (size_t)p.wslots * PL * p.BN * 128 + t3_misc_smem(p.BN, PL) : t3_fixed_smem(Kuse, p.BN, PL)) + (size_t)p.nstage * t3_stage_bytes(PL);
+    // Residual through a TMA ring (two-plane kernel): 32 KB of boxes [128 samples][32 columns] of the 3-D tensor (columns, node,
+    // sample), loaded by the otherwise idle warp 14 two chunks ahead of the epilogue.  192 -> 192 + tanh + residual: 435 -> 312 us
+    // (3.97 TB/s = 61 % of the HBM copy peak).  On the K = 256 layer (to_out) the ring lifts shared memory from 195 to 227 KB, past
+    // the 196 KB carve-out step that costs L1 (see t3_as_cfg), and still wins: 349 -> 316 us (SKELDIFF_T3_RES_TMA_MAX_KB=195 restores
+    // the old limit, SKELDIFF_T3_RES_TMA=0 the epilogue's own loads).
+    CUtensorMap mr = mw;
+    p.res_tma = 0;
+    {
+        static int res_env = -1;             // SKELDIFF_T3_RES_TMA=0: residual by the epilogue's own loads (A/B timing)
+        if (res_env < 0) { const char* e = getenv("SKELDIFF_T3_RES_TMA"); res_env = (e && e[0] == '0') ? 0 : 1; }
+        const size_t ring = (size_t)2 * T3_BM * 32 * sizeof(float);
+        static const int max_kb = t3_env("SKELDIFF_T3_RES_TMA_MAX_KB", 227);
+        if (res_env && has_res && PL == 2 && p.residual.rep == 1 && p.BN % 32 == 0 && smem + ring <= (size_t)max_kb * 1024) {
+            cuuint64_t rdims[3] = {(cuuint64_t)L->OUT, (cuuint64_t)L->N, (cuuint64_t)c.B};
+            cuuint64_t rstrides[2] = {(cuuint64_t)p.residual.sn * 4, (cuuint64_t)p.residual.sb * 4};
+            cuuint32_t rbox[3] = {32, 1, (cuuint32_t)T3_BM};
+            cuuint32_t restr[3] = {1, 1, 1};
+            CUresult rr = enc(&mr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.residual.ptr), rdims, rstrides, rbox, restr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (rr == CUDA_SUCCESS) { p.res_tma = 1; smem += ring; }
+        }
+    }
     const int sms = sm_count();
     long long gangs = p.a_stationary ? sms : sms / p.NT;
     if (gangs < 1) gangs = 1;
     if (gangs > (long long)p.N * p.MT) gangs = (long long)p.N * p.MT;
     const int grid = (int)(p.a_stationary ? gangs : gangs * p.NT);
 #define T3_DISPATCH(PLN) \
-    if (act == SD_ACT_NONE) return has_res ? t3_launch_t<SD_ACT_NONE, true, PLN>(mw, p, grid, smem, st) : t3_launch_t<SD_ACT_NONE, false, PLN>(mw, p, grid, smem, st); \
-    if (act == SD_ACT_TANH) return has_res ? t3_launch_t<SD_ACT_TANH, true, PLN>(mw, p, grid, smem, st) : t3_launch_t<SD_ACT_TANH, false, PLN>(mw, p, grid, smem, st); \
-    if (act == SD_ACT_TANH_TANH) return has_res ? t3_launch_t<SD_ACT_TANH_TANH, true, PLN>(mw, p, grid, smem, st) : t3_launch_t<SD_ACT_TANH_TANH, false, PLN>(mw, p, grid, smem, st);
+    if (act == SD_ACT_NONE) return has_res ? t3_launch_t<SD_ACT_NONE, true, PLN>(mw, mr, p, grid, smem, st) : t3_launch_t<SD_ACT_NONE, false, PLN>(mw, mr, p, grid, smem, st); \
+    if (act == SD_ACT_TANH) return has_res ? t3_launch_t<SD_ACT_TANH, true, PLN>(mw, mr, p, grid, smem, st) : t3_launch_t<SD_ACT_TANH, false, PLN>(mw, mr, p, grid, smem, st); \
+    if (act == SD_ACT_TANH_TANH) return has_res ? t3_launch_t<SD_ACT_TANH_TANH, true, PLN>(mw, mr, p, grid, smem, st) : t3_launch_t<SD_ACT_TANH_TANH, false, PLN>(mw, mr, p, grid, smem, st);
     if (PL == 2) { T3_DISPATCH(2) } else { T3_DISPATCH(3) }
 #undef T3_DISPATCH
     set_error("bf16x3 path: unknown activation %d", act);
