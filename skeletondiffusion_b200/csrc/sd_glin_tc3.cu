@@ -57,6 +57,7 @@ struct T3Params {
     int a_stationary;           // 1: the stage ring holds the whole K of an m-tile, n-tiles looped inside the CTA, weights streamed
     int wslots;                 // weight slots of the activation-stationary mode (2 .. T3_MAX_WSLOTS)
     int res_tma;                // 1: the residual tile rides a TMA ring (warp 14 -> two [128 rows][32 columns] boxes in shared memory)
+    int out_tma;                // 1: the output chunk leaves through a TMA store of the warp's staging tile (two-plane kernel)
     NodeTypes types;
     const float* row_scale;
     const float* bias_node;
@@ -92,6 +93,13 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
     hi = *reinterpret_cast<const uint32_t*>(&h);
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
+// Streaming 16-byte load of an activation granule: read once per CTA, so it does not allocate in L1 (the in-flight
+// granules of the 256 producer threads are 64 KB, most of the L1 left beside the shared-memory carve-out).
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
 // Bulk L2 prefetch: brings `bytes` (multiple of 16) at p into L2 without occupying registers or shared memory.
 __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
@@ -102,9 +110,17 @@ __device__ __forceinline__ uint32_t pack_hi(uint32_t a, uint32_t b) { return __b
 // FAST: tanh through MUFU.EX2 + MUFU.RCP (tc::tanh_ex2, ~1e-7 absolute) instead of libdevice tanhf (SKELDIFF_ACCURATE_EPILOGUE=1)
 template <bool FAST> __device__ __forceinline__ float t3_tanh(float x) { return FAST ? tanh_ex2(x) : tanhf(x); }
 
+// -DSD_T3_LDG_STREAM: activation granules with L1::no_allocate.  Measured within run-to-run noise of the allocating load
+// (192 -> 192 bare 228 vs 217 us, tanh 247 vs 253 us, sampling loop 199.5 vs 201.9 ms identity, 273.1 vs 271.6 ms dense): not enabled.
+#ifdef SD_T3_LDG_STREAM
+#define T3_LDA(p) ldg_stream(p)
+#else
+#define T3_LDA(p) __ldg(p)
+#endif
 template <int ACT, bool HAS_RES, bool FAST, int PL, bool RTMA>
 __global__ void __launch_bounds__(T3_THREADS, 1)
-glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_r, const T3Params p) {
+glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_o,
+                const T3Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment (SWIZZLE_128B atoms) by pointer arithmetic on the __shared__ array: rounding the address up through
     // uintptr_t made the compiler lose the address space and emit generic LD/ST for every shared-memory access of the kernel.
@@ -185,13 +201,13 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int b = b0 + 16 * i;
-                    v[i] = (b < b_end) ? __ldg(reinterpret_cast<const float4*>(base + (long long)b * seg.sb)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[i] = (b < b_end) ? T3_LDA(reinterpret_cast<const float4*>(base + (long long)b * seg.sb)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int b = b0 + 16 * i;
-                    v[i] = (b < b_end) ? __ldg(reinterpret_cast<const float4*>(base + (long long)(b / seg.rep) * seg.sb)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[i] = (b < b_end) ? T3_LDA(reinterpret_cast<const float4*>(base + (long long)(b / seg.rep) * seg.sb)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
             if (++f_kb == p.KB) { f_kb = 0; if (++f_mt == p.MT) { f_mt = 0; ++f_node; } }
@@ -422,6 +438,9 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                     for (int j = 0; j < J; ++j)
                         pp[j] = (bT0 + RPI * j < p.B) ? __ldg(reinterpret_cast<const float4*>(pre_base + (long long)(bT0 + RPI * j) * p.pre.sb + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
+                if (PL == 2 && p.out_tma) {                    // the previous chunk's bulk store has read the staging tile
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                }
                 __syncwarp();                                   // the previous chunk has been read out of the staging tile
 #pragma unroll
                 for (int hf = 0; hf < CW / 16; ++hf) {              // 16 columns at a time: v + vc stay within 32 registers
@@ -486,16 +505,34 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                                 rr[AHEAD - 1][j] = __ldg(reinterpret_cast<const float4*>(res_base + res_off[j] + c0 + CW * AHEAD));
                     }
                 }
+                if (PL == 2 && p.out_tma) {
+                    // Output through the copy engine: the results go back into the (now free) staging tile in plain row-major order
+                    // (a warp instruction writes 4 rows x 128 contiguous bytes: conflict-free) and ONE bulk tensor store moves the
+                    // [32 rows][32 columns] box to the 3-D output tensor (columns, node, sample); rows beyond the batch are clipped
+                    // by the tensor map.  The epilogue warps issue no global stores at all.
+                    __syncwarp();                               // every lane has read its transposed values
 #pragma unroll
-                for (int j = 0; j < J; ++j) {
-                    const int bj = bT0 + RPI * j;
-                    if (bj < p.B) *reinterpret_cast<float4*>(out_base + (long long)bj * p.out.sb + c0) = o[j];
+                    for (int j = 0; j < J; ++j) *reinterpret_cast<float4*>(stg + (tr + RPI * j) * CW + 4 * tcl) = o[j];
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                                     :: "l"(&map_o), "r"(smem_u32(stg)), "r"(o0 + c0), "r"(node), "r"(mt * T3_BM + quarter * 32) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < J; ++j) {
+                        const int bj = bT0 + RPI * j;
+                        if (bj < p.B) *reinterpret_cast<float4*>(out_base + (long long)bj * p.out.sb + c0) = o[j];
+                    }
                 }
             }
             tc_fence_before();
             mbar_arrive(&bars->acc_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (PL == 2 && p.out_tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");    // shared memory outlives the stores
     }
     tc_fence_before();
     __syncthreads();
@@ -559,14 +596,14 @@ int tc_split_planes() { return tl_split_planes; }
 void set_tc_split_planes(int planes) { tl_split_planes = planes == 2 ? 2 : 3; }
 
 template <int ACT, bool HAS_RES, int PL, bool FAST = false, bool RTMA = false>
-static int t3_launch_t(const CUtensorMap& mw, const CUtensorMap& mr, const T3Params& p, int grid, size_t smem, cudaStream_t st) {
+static int t3_launch_t(const CUtensorMap& mw, const CUtensorMap& mr, const CUtensorMap& mo, const T3Params& p, int grid, size_t smem, cudaStream_t st) {
     // the libdevice epilogue is kept for the three-plane kernel only (SKELDIFF_ACCURATE_EPILOGUE=1)
-    if (ACT != SD_ACT_NONE && !FAST && (PL == 2 || fast_epilogue())) return t3_launch_t<ACT, HAS_RES, PL, ACT != SD_ACT_NONE, RTMA>(mw, mr, p, grid, smem, st);
-    if (HAS_RES && PL == 2 && !RTMA && p.res_tma) return t3_launch_t<ACT, HAS_RES, PL, FAST, HAS_RES && PL == 2>(mw, mr, p, grid, smem, st);
+    if (ACT != SD_ACT_NONE && !FAST && (PL == 2 || fast_epilogue())) return t3_launch_t<ACT, HAS_RES, PL, ACT != SD_ACT_NONE, RTMA>(mw, mr, mo, p, grid, smem, st);
+    if (HAS_RES && PL == 2 && !RTMA && p.res_tma) return t3_launch_t<ACT, HAS_RES, PL, FAST, HAS_RES && PL == 2>(mw, mr, mo, p, grid, smem, st);
     auto kern = glin_tc3_kernel<ACT, HAS_RES, FAST, PL, RTMA>;
     static unsigned long long configured = 0;      // bit d: attribute set on device d (it is per device)
     if (int rc_attr = opt_in_smem(kern, (size_t)((227 * 1024)), configured)) return rc_attr;
-    kern<<<grid, T3_THREADS, smem, st>>>(mw, mr, p);
+    kern<<<grid, T3_THREADS, smem, st>>>(mw, mr, mo, p);
     SD_LAUNCH_OK("glin_tc3_kernel");
     return SD_OK;
 }
@@ -655,15 +692,31 @@ static int t3_launch_one(const sd_glin* L, const GlinCall& c, const ViewW& out, 
             if (rr == CUDA_SUCCESS) { p.res_tma = 1; smem += ring; }
         }
     }
+    // Output through TMA stores (two-plane kernel): the output is a 3-D tensor (columns, node, sample) like the residual.
+    CUtensorMap mo = mw;
+    p.out_tma = 0;
+    {
+        static int out_env = -1;             // SKELDIFF_T3_OUT_TMA=0: output by the epilogue's STG.128 (A/B timing)
+        if (out_env < 0) { const char* e = getenv("SKELDIFF_T3_OUT_TMA"); out_env = (e && e[0] == '0') ? 0 : 1; }
+        if (out_env && PL == 2 && out.rep == 1 && p.BN % 32 == 0) {
+            cuuint64_t odims[3] = {(cuuint64_t)L->OUT, (cuuint64_t)L->N, (cuuint64_t)c.B};
+            cuuint64_t ostrides[2] = {(cuuint64_t)out.sn * 4, (cuuint64_t)out.sb * 4};
+            cuuint32_t obox[3] = {32, 1, 32};
+            cuuint32_t oestr[3] = {1, 1, 1};
+            CUresult ro = enc(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, out.ptr, odims, ostrides, obox, oestr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (ro == CUDA_SUCCESS) p.out_tma = 1;
+        }
+    }
     const int sms = sm_count();
     long long gangs = p.a_stationary ? sms : sms / p.NT;
     if (gangs < 1) gangs = 1;
     if (gangs > (long long)p.N * p.MT) gangs = (long long)p.N * p.MT;
     const int grid = (int)(p.a_stationary ? gangs : gangs * p.NT);
 #define T3_DISPATCH(PLN) \
-    if (act == SD_ACT_NONE) return has_res ? t3_launch_t<SD_ACT_NONE, true, PLN>(mw, mr, p, grid, smem, st) : t3_launch_t<SD_ACT_NONE, false, PLN>(mw, mr, p, grid, smem, st); \
-    if (act == SD_ACT_TANH) return has_res ? t3_launch_t<SD_ACT_TANH, true, PLN>(mw, mr, p, grid, smem, st) : t3_launch_t<SD_ACT_TANH, false, PLN>(mw, mr, p, grid, smem, st); \
-    if (act == SD_ACT_TANH_TANH) return has_res ? t3_launch_t<SD_ACT_TANH_TANH, true, PLN>(mw, mr, p, grid, smem, st) : t3_launch_t<SD_ACT_TANH_TANH, false, PLN>(mw, mr, p, grid, smem, st);
+    if (act == SD_ACT_NONE) return has_res ? t3_launch_t<SD_ACT_NONE, true, PLN>(mw, mr, mo, p, grid, smem, st) : t3_launch_t<SD_ACT_NONE, false, PLN>(mw, mr, mo, p, grid, smem, st); \
+    if (act == SD_ACT_TANH) return has_res ? t3_launch_t<SD_ACT_TANH, true, PLN>(mw, mr, mo, p, grid, smem, st) : t3_launch_t<SD_ACT_TANH, false, PLN>(mw, mr, mo, p, grid, smem, st); \
+    if (act == SD_ACT_TANH_TANH) return has_res ? t3_launch_t<SD_ACT_TANH_TANH, true, PLN>(mw, mr, mo, p, grid, smem, st) : t3_launch_t<SD_ACT_TANH_TANH, false, PLN>(mw, mr, mo, p, grid, smem, st);
     if (PL == 2) { T3_DISPATCH(2) } else { T3_DISPATCH(3) }
 #undef T3_DISPATCH
     set_error("bf16x3 path: unknown activation %d", act);
