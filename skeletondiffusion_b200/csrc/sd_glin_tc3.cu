@@ -58,6 +58,7 @@ struct T3Params {
     int wslots;                 // weight slots of the activation-stationary mode (2 .. T3_MAX_WSLOTS)
     int res_tma;                // 1: the residual tile rides a TMA ring (warp 14 -> two [128 rows][32 columns] boxes in shared memory)
     int out_tma;                // 1: the output chunk leaves through a TMA store of the warp's staging tile (two-plane kernel)
+    int raw_slots;              // ATMA: fp32 activation k-blocks arrive by TMA in a ring of [128 rows][64 floats] boxes (warp 15)
     NodeTypes types;
     const float* row_scale;
     const float* bias_node;
@@ -72,6 +73,7 @@ struct __align__(8) T3Barriers {
     uint64_t ws_full[T3_MAX_WSLOTS], ws_empty[T3_MAX_WSLOTS];       // weight slots (activation-stationary mode)
     uint64_t acc_full[2], acc_empty[2];
     uint64_t res_full[2], res_empty[2];     // residual chunk ring (res_tma)
+    uint64_t raw_full[4], raw_empty[4];     // fp32 activation ring (ATMA)
     uint32_t tmem_base, pad;
 };
 
@@ -117,10 +119,10 @@ template <bool FAST> __device__ __forceinline__ float t3_tanh(float x) { return 
 #else
 #define T3_LDA(p) __ldg(p)
 #endif
-template <int ACT, bool HAS_RES, bool FAST, int PL, bool RTMA>
+template <int ACT, bool HAS_RES, bool FAST, int PL, bool RTMA, bool ATMA>
 __global__ void __launch_bounds__(T3_THREADS, 1)
 glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_o,
-                const T3Params p) {
+                const __grid_constant__ CUtensorMap map_a, const T3Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment (SWIZZLE_128B atoms) by pointer arithmetic on the __shared__ array: rounding the address up through
     // uintptr_t made the compiler lose the address space and emit generic LD/ST for every shared-memory access of the kernel.
@@ -134,7 +136,9 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
     float* epi_stage = epi_add + p.BN;                             // 4 warps x [32 rows][16 or 32 floats], swizzled
     float* res_buf = epi_stage + 4 * 32 * t3_chunk_cols(PL);       // res_tma: 2 x [128 rows][32 floats]
     constexpr int RES_BOX = T3_BM * 32;
-    T3Barriers* bars = reinterpret_cast<T3Barriers*>(res_buf + (RTMA ? 2 * RES_BOX : 0));
+    float* a_raw = res_buf + (RTMA ? 2 * RES_BOX : 0);             // ATMA: raw_slots x [128 rows][64 floats]
+    constexpr int RAW_BOX = T3_BM * T3_BK;
+    T3Barriers* bars = reinterpret_cast<T3Barriers*>(a_raw + (ATMA ? p.raw_slots * RAW_BOX : 0));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -145,6 +149,7 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
         for (int s = 0; s < T3_MAX_WSLOTS; ++s) { mbar_init(&bars->ws_full[s], 1); mbar_init(&bars->ws_empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&bars->acc_full[s], 1); mbar_init(&bars->acc_empty[s], 128); }
         for (int s = 0; s < 2; ++s) { mbar_init(&bars->res_full[s], 1); mbar_init(&bars->res_empty[s], 4); }
+        for (int s = 0; s < 4; ++s) { mbar_init(&bars->raw_full[s], 1); mbar_init(&bars->raw_empty[s], 8); }
         fence_barrier_init();
     }
     if (warp == T3_ALLOC_WARP) tmem_alloc(&bars->tmem_base, (uint32_t)p.tmem_cols);
@@ -240,11 +245,31 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
             mbar_arrive(&bars->full[stage]);
             if (++stage == p.nstage) { stage = 0; phase ^= 1; }
         };
+        if (ATMA) {
+            // The fp32 k-blocks arrive by TMA (warp 15) in a ring of [128 rows][64 floats] boxes: the producers read their eight
+            // granules from shared memory (a warp instruction covers two whole 256-byte rows: conflict-free), hand the box back
+            // and split as before.  No global load is issued by these warps: their loads used to be the first consumer to wait
+            // (10 % of the kernel's stall samples sat on the F2FP that follows the LDG batch).
+            uint32_t rs = 0, rph = 0;
+            for (long long q = 0; q < q_end; ++q) {
+                float4 v[8];
+                mbar_wait(&bars->raw_full[rs], rph);
+                const float* box = a_raw + (size_t)rs * RAW_BOX + col4 * 4;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(box + (row0 + 16 * i) * T3_BK);
+                fence_proxy_async();                 // the reads are ordered before the copy engine's refill of the box
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->raw_empty[rs]);
+                if (++rs == (uint32_t)p.raw_slots) { rs = 0; rph ^= 1u; }
+                emit(v);
+            }
+        } else {
         float4 va[8], vb[8];
         fetch(va);
         for (long long q = 0; q < q_end; q += 2) {
             fetch(vb); emit(va);
             fetch(va); emit(vb);
+        }
         }
     } else if (warp >= 12) {
       // warpgroup 3 (MMA issue, weight loader, two idle warps) hands registers over to the epilogue warpgroup
@@ -337,6 +362,23 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                                         pl * p.n_types + type);
                         if (++slot == (uint32_t)p.wslots) { slot = 0; ph ^= 1u; }
                     }
+            }
+        }
+        __syncwarp();
+      } else if (warp == T3_WLOAD_WARP + 2) {
+        // ================================================================ fp32 activation ring (ATMA): one [128 samples][64 k] box per
+        // (tile, k-block) in the producers' order; columns beyond K are zero-filled by the tensor map (K = 96: half of the 2nd block)
+        if (ATMA && lane == 0) {
+            tma_prefetch_desc(&map_a);
+            uint32_t rs = 0, rph = 0;
+            for (long long it = item_lo; it < item_hi; ++it) {
+                const int node = (int)(it / p.MT), mt = (int)(it % p.MT);
+                for (int kb = 0; kb < p.KB; ++kb) {
+                    mbar_wait(&bars->raw_empty[rs], rph ^ 1u);
+                    mbar_arrive_expect_tx(&bars->raw_full[rs], (uint32_t)RAW_BOX * 4u);
+                    tma_load_3d(a_raw + (size_t)rs * RAW_BOX, &map_a, &bars->raw_full[rs], kb * T3_BK, node, mt * T3_BM);
+                    if (++rs == (uint32_t)p.raw_slots) { rs = 0; rph ^= 1u; }
+                }
             }
         }
         __syncwarp();
@@ -595,15 +637,16 @@ static thread_local int tl_split_planes = 3;
 int tc_split_planes() { return tl_split_planes; }
 void set_tc_split_planes(int planes) { tl_split_planes = planes == 2 ? 2 : 3; }
 
-template <int ACT, bool HAS_RES, int PL, bool FAST = false, bool RTMA = false>
-static int t3_launch_t(const CUtensorMap& mw, const CUtensorMap& mr, const CUtensorMap& mo, const T3Params& p, int grid, size_t smem, cudaStream_t st) {
+template <int ACT, bool HAS_RES, int PL, bool FAST = false, bool RTMA = false, bool ATMA = false>
+static int t3_launch_t(const CUtensorMap& mw, const CUtensorMap& mr, const CUtensorMap& mo, const CUtensorMap& ma, const T3Params& p, int grid, size_t smem, cudaStream_t st) {
     // the libdevice epilogue is kept for the three-plane kernel only (SKELDIFF_ACCURATE_EPILOGUE=1)
-    if (ACT != SD_ACT_NONE && !FAST && (PL == 2 || fast_epilogue())) return t3_launch_t<ACT, HAS_RES, PL, ACT != SD_ACT_NONE, RTMA>(mw, mr, mo, p, grid, smem, st);
-    if (HAS_RES && PL == 2 && !RTMA && p.res_tma) return t3_launch_t<ACT, HAS_RES, PL, FAST, HAS_RES && PL == 2>(mw, mr, mo, p, grid, smem, st);
-    auto kern = glin_tc3_kernel<ACT, HAS_RES, FAST, PL, RTMA>;
+    if (ACT != SD_ACT_NONE && !FAST && (PL == 2 || fast_epilogue())) return t3_launch_t<ACT, HAS_RES, PL, ACT != SD_ACT_NONE, RTMA, ATMA>(mw, mr, mo, ma, p, grid, smem, st);
+    if (HAS_RES && PL == 2 && !RTMA && p.res_tma) return t3_launch_t<ACT, HAS_RES, PL, FAST, HAS_RES && PL == 2, ATMA>(mw, mr, mo, ma, p, grid, smem, st);
+    if (!HAS_RES && PL == 2 && !ATMA && p.raw_slots) return t3_launch_t<ACT, HAS_RES, PL, FAST, RTMA, !HAS_RES && PL == 2>(mw, mr, mo, ma, p, grid, smem, st);
+    auto kern = glin_tc3_kernel<ACT, HAS_RES, FAST, PL, RTMA, ATMA>;
     static unsigned long long configured = 0;      // bit d: attribute set on device d (it is per device)
     if (int rc_attr = opt_in_smem(kern, (size_t)((227 * 1024)), configured)) return rc_attr;
-    kern<<<grid, T3_THREADS, smem, st>>>(mw, mr, mo, p);
+    kern<<<grid, T3_THREADS, smem, st>>>(mw, mr, mo, ma, p);
     SD_LAUNCH_OK("glin_tc3_kernel");
     return SD_OK;
 }
@@ -708,15 +751,35 @@ static int t3_launch_one(const sd_glin* L, const GlinCall& c, const ViewW& out, 
             if (ro == CUDA_SUCCESS) p.out_tma = 1;
         }
     }
+    // fp32 activations through a TMA ring (two-plane kernel without a residual, one K segment read in place): as many 32 KB
+    // boxes as fit (2 .. 4); the producers then issue no global loads at all.
+    CUtensorMap ma = mw;
+    p.raw_slots = 0;
+    {
+        static int a_env = -1;               // SKELDIFF_T3_A_TMA=0: activations by the producers' own loads (A/B timing)
+        if (a_env < 0) { const char* e = getenv("SKELDIFF_T3_A_TMA"); a_env = (e && e[0] == '0') ? 0 : 1; }
+        const size_t box = (size_t)T3_BM * T3_BK * sizeof(float);
+        int slots = (int)(((size_t)227 * 1024 - smem) / box);
+        if (slots > 4) slots = 4;
+        if (a_env && PL == 2 && !has_res && K1 == 0 && c.a0.rep == 1 && slots >= 2) {
+            cuuint64_t adims[3] = {(cuuint64_t)K0, (cuuint64_t)L->N, (cuuint64_t)c.B};
+            cuuint64_t astrides[2] = {(cuuint64_t)c.a0.sn * 4, (cuuint64_t)c.a0.sb * 4};
+            cuuint32_t abox[3] = {(cuuint32_t)T3_BK, 1, (cuuint32_t)T3_BM};
+            cuuint32_t aestr[3] = {1, 1, 1};
+            CUresult ra = enc(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(c.a0.ptr), adims, astrides, abox, aestr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (ra == CUDA_SUCCESS) { p.raw_slots = slots; smem += (size_t)slots * box; }
+        }
+    }
     const int sms = sm_count();
     long long gangs = p.a_stationary ? sms : sms / p.NT;
     if (gangs < 1) gangs = 1;
     if (gangs > (long long)p.N * p.MT) gangs = (long long)p.N * p.MT;
     const int grid = (int)(p.a_stationary ? gangs : gangs * p.NT);
 #define T3_DISPATCH(PLN) \
-    if (act == SD_ACT_NONE) return has_res ? t3_launch_t<SD_ACT_NONE, true, PLN>(mw, mr, mo, p, grid, smem, st) : t3_launch_t<SD_ACT_NONE, false, PLN>(mw, mr, mo, p, grid, smem, st); \
-    if (act == SD_ACT_TANH) return has_res ? t3_launch_t<SD_ACT_TANH, true, PLN>(mw, mr, mo, p, grid, smem, st) : t3_launch_t<SD_ACT_TANH, false, PLN>(mw, mr, mo, p, grid, smem, st); \
-    if (act == SD_ACT_TANH_TANH) return has_res ? t3_launch_t<SD_ACT_TANH_TANH, true, PLN>(mw, mr, mo, p, grid, smem, st) : t3_launch_t<SD_ACT_TANH_TANH, false, PLN>(mw, mr, mo, p, grid, smem, st);
+    if (act == SD_ACT_NONE) return has_res ? t3_launch_t<SD_ACT_NONE, true, PLN>(mw, mr, mo, ma, p, grid, smem, st) : t3_launch_t<SD_ACT_NONE, false, PLN>(mw, mr, mo, ma, p, grid, smem, st); \
+    if (act == SD_ACT_TANH) return has_res ? t3_launch_t<SD_ACT_TANH, true, PLN>(mw, mr, mo, ma, p, grid, smem, st) : t3_launch_t<SD_ACT_TANH, false, PLN>(mw, mr, mo, ma, p, grid, smem, st); \
+    if (act == SD_ACT_TANH_TANH) return has_res ? t3_launch_t<SD_ACT_TANH_TANH, true, PLN>(mw, mr, mo, ma, p, grid, smem, st) : t3_launch_t<SD_ACT_TANH_TANH, false, PLN>(mw, mr, mo, ma, p, grid, smem, st);
     if (PL == 2) { T3_DISPATCH(2) } else { T3_DISPATCH(3) }
 #undef T3_DISPATCH
     set_error("bf16x3 path: unknown activation %d", act);
