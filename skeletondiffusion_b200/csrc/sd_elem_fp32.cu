@@ -271,6 +271,8 @@ mahalanobis_loss_kernel(const float* __restrict__ out, const float* __restrict__
 // GRU gates (recurrent.py:351-358): r = sig(xr_r+hr_r); z = sig(xr_z+hr_z); n = tanh(xr_n + r*hr_n)
 //                                   h' = n - n*z + z*h            (clock mask == 1, clockwork=False)
 // =============================================================================================
+// FAST: sigmoid / tanh through MUFU.EX2 + MUFU.RCP (~1e-7 absolute, as in the per-sample kernels of sd_mix.cu) instead of libdevice
+template <bool FAST>
 __global__ void __launch_bounds__(256)
 gru_gates_kernel(const View xr, const float* __restrict__ xr_bias, const float* __restrict__ hr,
                  const float* __restrict__ hr_bias, const View h_in, const ViewW h_out, int B, int N, int H) {
@@ -297,10 +299,15 @@ gru_gates_kernel(const View xr, const float* __restrict__ xr_bias, const float* 
         }
     }
     const float4 hx = __ldg(reinterpret_cast<const float4*>(row_ptr(h_in, b, n) + j));
-    auto sig = [](float v) { return 1.0f / (1.0f + expf(-v)); };
+    auto sig = [](float v) { return FAST ? __fdividef(1.0f, 1.0f + exp2f(-1.4426950408889634f * v)) : 1.0f / (1.0f + expf(-v)); };
+    auto th = [](float v) {
+        if (!FAST) return tanhf(v);
+        const float t = exp2f(-2.8853900817779268f * fabsf(v));
+        return copysignf(__fdividef(1.0f - t, 1.0f + t), v);
+    };
     auto cell = [&](float ir, float iz, float in_, float hr_, float hz, float hn, float hprev) {
         const float r = sig(ir + hr_), z = sig(iz + hz);
-        const float nn = tanhf(in_ + r * hn);
+        const float nn = th(in_ + r * hn);
         return nn - nn * z + z * hprev;
     };
     float4 o;
@@ -312,11 +319,12 @@ gru_gates_kernel(const View xr, const float* __restrict__ xr_bias, const float* 
 }
 
 int gru_gates_fp32(const View& xr, const float* xr_bias, const float* hr, const float* hr_bias,
-                   const View& h_in, const ViewW& h_out, int B, int N, int H, cudaStream_t st) {
+                   const View& h_in, const ViewW& h_out, int B, int N, int H, cudaStream_t st, bool fast) {
     if (B <= 0) return SD_OK;
     if (H % 4 != 0) { set_error("gru: hidden %d must be a multiple of 4", H); return SD_ERR_UNSUPPORTED; }
     const long long total = (long long)B * N * (H >> 2);
-    gru_gates_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(xr, xr_bias, hr, hr_bias, h_in, h_out, B, N, H);
+    if (fast) gru_gates_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(xr, xr_bias, hr, hr_bias, h_in, h_out, B, N, H);
+    else gru_gates_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(xr, xr_bias, hr, hr_bias, h_in, h_out, B, N, H);
     SD_LAUNCH_OK("gru_gates_kernel");
     return SD_OK;
 }

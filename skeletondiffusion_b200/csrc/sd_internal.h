@@ -144,6 +144,6 @@ bool node_attention_mix_supported(int N, int heads, int dh, const float* qkv, co
 int node_attention_mix_fp32(const float* G_host, const float* row_scale, const float* qkv, float* out, int B, int N, int heads, int dh, cudaStream_t st);
 int add_residual_fp32(float* out, const View& res, int B, int N, int OUT, long long out_sb, long long out_sn, cudaStream_t st);
 int gru_gates_fp32(const View& xr, const float* xr_bias, const float* hr, const float* hr_bias,
-                   const View& h_in, const ViewW& h_out, int B, int N, int H, cudaStream_t st);
+                   const View& h_in, const ViewW& h_out, int B, int N, int H, cudaStream_t st, bool fast = false);
 
 }  // namespace sd
