@@ -533,12 +533,98 @@ static int ghd_launch(const float* G_dev, const float* Wfc, const float* bias_no
     return SD_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Tiled variant of the output head (the default): a CTA stages the h rows of a few whole samples in shared memory with
+// coalesced loads (row stride H + 1: conflict-free for the row-per-thread dots), W_fc of every node type and G^ next to them;
+// thread = (row, output) dot product over H, then thread = (sample, node, output) for the N x N mix, bias, activation.
+// No shuffle trees, 4-byte stores of 3 floats per row are the only uncoalesced access.  Reads h once: HBM-bound.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int GH2_THREADS = 256;
+__global__ void __launch_bounds__(GH2_THREADS)
+gru_head_tiled_kernel(const float* __restrict__ G, const float* __restrict__ Wfc, const float* __restrict__ bias_node, const NodeTypes types,
+                      int N, int H, int F, int n_types, int spb, const View h, const ViewW out, int act, int B) {
+    extern __shared__ float gh2[];
+    const int LD = H + 1, rows_max = spb * N;
+    float* h_s = gh2;                                   // [spb * N][H + 1]
+    float* w_s = h_s + (size_t)rows_max * LD;           // [n_types * F][H + 1]
+    float* g_s = w_s + (size_t)n_types * F * LD;        // [N][N] (when G)
+    float* p_s = g_s + (G ? N * N : 0);                 // [spb * N][F]
+    for (int i = threadIdx.x; i < n_types * F * H; i += GH2_THREADS) w_s[(i / H) * LD + i % H] = __ldg(Wfc + i);
+    if (G) for (int i = threadIdx.x; i < N * N; i += GH2_THREADS) g_s[i] = __ldg(G + i);
+    const int h4 = H >> 2;
+    for (long long b0 = (long long)blockIdx.x * spb; b0 < B; b0 += (long long)gridDim.x * spb) {
+        const int ns = (int)min((long long)spb, (long long)B - b0), rows = ns * N;
+        __syncthreads();                                // previous tile consumed (also orders the W / G fill)
+        for (int i = threadIdx.x; i < rows * h4; i += GH2_THREADS) {
+            const int r = i / h4, q = i - r * h4;
+            const int bl = r / N, n = r - bl * N;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(row_ptr(h, (int)(b0 + bl), n) + 4 * q));
+            float* d = h_s + r * LD + 4 * q;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < rows * F; i += GH2_THREADS) {
+            const int f = i / rows, r = i - f * rows;   // consecutive threads = consecutive rows (distinct banks), same output
+            const int n = r % N;
+            const float* hv = h_s + r * LD;
+            const float* wv = w_s + (types.t[n] * F + f) * LD;
+            float a0 = 0.f, a1 = 0.f;
+            for (int u = 0; u + 1 < H; u += 2) { a0 = fmaf(hv[u], wv[u], a0); a1 = fmaf(hv[u + 1], wv[u + 1], a1); }
+            if (H & 1) a0 = fmaf(hv[H - 1], wv[H - 1], a0);
+            p_s[r * F + f] = a0 + a1;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < rows * F; i += GH2_THREADS) {
+            const int r = i / F, f = i - r * F;
+            const int bl = r / N, n = r - bl * N;
+            float v;
+            if (G) {
+                v = 0.f;
+                for (int m = 0; m < N; ++m) v = fmaf(g_s[n * N + m], p_s[(bl * N + m) * F + f], v);
+            } else {
+                v = p_s[r * F + f];
+            }
+            if (bias_node) v += __ldg(bias_node + n * F + f);
+            if (act == SD_ACT_TANH) v = tanhf(v);
+            out.ptr[(b0 + bl) * out.sb + (long long)n * out.sn + f] = v;
+        }
+    }
+}
+
+static int gru_head_tiled(const float* G_dev, const float* Wfc, const float* bias_node, const NodeTypes& types, int n_types, int N, int H, int F,
+                          const View& h, const ViewW& out, int act, int B, cudaStream_t st, bool* used) {
+    *used = false;
+    if (H % 4 || h.rep != 1 || (reinterpret_cast<uintptr_t>(h.ptr) & 15u) || h.sb % 4 || h.sn % 4) return SD_OK;
+    int spb = 96 / N; if (spb < 1) spb = 1;
+    const size_t smem = ((size_t)spb * N * (H + 1) + (size_t)n_types * F * (H + 1) + (G_dev ? N * N : 0) + (size_t)spb * N * F) * sizeof(float);
+    if (smem > 100 * 1024) return SD_OK;
+    static unsigned long long configured = 0;
+    if (smem > 48 * 1024) if (int rc = opt_in_smem(gru_head_tiled_kernel, 100 * 1024, configured)) return rc;
+    long long grid = ((long long)B + spb - 1) / spb;
+    const long long cap = (long long)sm_count() * 8;
+    if (grid > cap) grid = cap;
+    gru_head_tiled_kernel<<<(unsigned)grid, GH2_THREADS, smem, st>>>(G_dev, Wfc, bias_node, types, N, H, F, n_types, spb, h, out, act, B);
+    count_launch();
+    if (check_cuda(cudaGetLastError(), "gru_head_tiled_kernel")) return SD_ERR_CUDA;
+    *used = true;
+    return SD_OK;
+}
+
 bool gru_head_supported(int N, int H, int F) { return (N == 16 || N == 17 || N == 21) && F >= 1 && F <= 3 && H <= 512; }
 
 // G_dev: fc's normalised graph influence [N][N] on the device, or null for the identity
 int gru_head_fp32(const float* G_dev, const float* Wfc, const float* bias_node, const NodeTypes& types, int n_types, int N, int H, int F,
                   const View& h, const ViewW& out, int act, int B, cudaStream_t st) {
     if (B <= 0) return SD_OK;
+    {
+        static int tiled_env = -1;           // SKELDIFF_GRU_HEAD_TILED=0: the warp-per-sample shuffle kernel (A/B timing)
+        if (tiled_env < 0) { const char* e = getenv("SKELDIFF_GRU_HEAD_TILED"); tiled_env = (e && e[0] == '0') ? 0 : 1; }
+        if (tiled_env) {
+            bool used = false;
+            if (int rc = gru_head_tiled(G_dev, Wfc, bias_node, types, n_types, N, H, F, h, out, act, B, st, &used)) return rc;
+            if (used) return SD_OK;
+        }
+    }
 #define SD_GHD(NN) if (N == NN) { \
         if (F == 3) return ghd_launch<NN, 3>(G_dev, Wfc, bias_node, types, n_types, H, h, out, act, B, st); \
         if (F == 2) return ghd_launch<NN, 2>(G_dev, Wfc, bias_node, types, n_types, H, h, out, act, B, st); \
