@@ -59,6 +59,7 @@ struct T3Params {
     int res_tma;                // 1: the residual tile rides a TMA ring (warp 14 -> two [128 rows][32 columns] boxes in shared memory)
     int out_tma;                // 1: the output chunk leaves through a TMA store of the warp's staging tile (two-plane kernel)
     int raw_slots;              // ATMA: fp32 activation k-blocks arrive by TMA in a ring of [128 rows][64 floats] boxes (warp 15)
+    int stg2;                   // 1: two staging tiles per epilogue warp (a chunk's bulk store overlaps the next chunk)
     NodeTypes types;
     const float* row_scale;
     const float* bias_node;
@@ -134,7 +135,7 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
     float* epi_mul = reinterpret_cast<float*>(a_smem + (size_t)p.nstage * STAGE_BYTES);
     float* epi_add = epi_mul + p.BN;
     float* epi_stage = epi_add + p.BN;                             // 4 warps x [32 rows][16 or 32 floats], swizzled
-    float* res_buf = epi_stage + 4 * 32 * t3_chunk_cols(PL);       // res_tma: 2 x [128 rows][32 floats]
+    float* res_buf = epi_stage + (p.stg2 ? 2 : 1) * 4 * 32 * t3_chunk_cols(PL);       // res_tma: 2 x [128 rows][32 floats]
     constexpr int RES_BOX = T3_BM * 32;
     float* a_raw = res_buf + (RTMA ? 2 * RES_BOX : 0);             // ATMA: raw_slots x [128 rows][64 floats]
     constexpr int RAW_BOX = T3_BM * T3_BK;
@@ -411,7 +412,9 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
         // LDG / STG.128 of the warp touches RPI rows and J instructions cover the 32 rows of the warp's lane quarter.
         // CW = 32 (two planes: shared memory to spare): 128 contiguous bytes per row = whole L2 lines; CW = 16 (three planes): 64.
         constexpr int CW = t3_chunk_cols(PL), LPR = CW / 4, RPI = 32 / LPR, J = 32 / RPI, AHEAD = (CW == 32) ? 2 : T3_RES_AHEAD;
-        float* stg = epi_stage + quarter * (32 * CW);
+        float* stg0 = epi_stage + quarter * (32 * CW);
+        float* stg = stg0;
+        uint32_t stg_flip = 0;
         const int tr = lane / LPR, tcl = lane % LPR;
         uint32_t acc = 0, acc_phase = 0;
         uint32_t r_slot = 0, r_phase = 0;                          // residual chunk ring (res_tma)
@@ -480,8 +483,14 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                     for (int j = 0; j < J; ++j)
                         pp[j] = (bT0 + RPI * j < p.B) ? __ldg(reinterpret_cast<const float4*>(pre_base + (long long)(bT0 + RPI * j) * p.pre.sb + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                if (PL == 2 && p.out_tma) {                    // the previous chunk's bulk store has read the staging tile
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                if (PL == 2 && p.out_tma) {                    // the bulk store that last used this staging tile has read it
+                    if (p.stg2) {
+                        stg = stg0 + (stg_flip ? 4 * 32 * CW : 0);
+                        stg_flip ^= 1u;
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    } else {
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
                 }
                 __syncwarp();                                   // the previous chunk has been read out of the staging tile
 #pragma unroll
@@ -713,6 +722,15 @@ static int t3_launch_one(const sd_glin* L, const GlinCall& c, const ViewW& out, 
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (weights x3) failed: %d", (int)r); return SD_ERR_CUDA; }
     size_t smem = (p.a_stationary ? (size_t)p.wslots * PL * p.BN * 128 + t3_misc_smem(p.BN, PL) : t3_fixed_smem(Kuse, p.BN, PL)) + (size_t)p.nstage * t3_stage_bytes(PL);
+    // Two staging tiles per epilogue warp (two-plane kernel, output through bulk stores): the store of chunk c overlaps chunk
+    // c + 1 instead of being waited for at its start.  16 KB; taken first on wide outputs (many chunks per activation tile).
+    p.stg2 = 0;
+    {
+        static int s2_env = -1;              // SKELDIFF_T3_STG2=0/1/2: never / wide outputs only (default) / whenever it fits
+        if (s2_env < 0) { const char* e = getenv("SKELDIFF_T3_STG2"); s2_env = (e && e[0]) ? atoi(e) : 1; }
+        const size_t extra = (size_t)4 * 32 * 32 * sizeof(float);
+        if (PL == 2 && s2_env && (s2_env == 2 || p.NT >= 4) && smem + extra <= (size_t)227 * 1024) { p.stg2 = 1; smem += extra; }
+    }
     // Residual through a TMA ring (two-plane kernel): 32 KB of boxes [128 samples][32 columns] of the 3-D tensor (columns, node,
     // sample), loaded by the otherwise idle warp 14 two chunks ahead of the epilogue.  192 -> 192 + tanh + residual: 435 -> 312 us
     // (3.97 TB/s = 61 % of the HBM copy peak).  On the K = 256 layer (to_out) the ring lifts shared memory from 195 to 227 KB, past
