@@ -197,16 +197,20 @@ int  sd_gru_create(int num_nodes, const int32_t* node_types_host, int n_types, i
                    int hidden_size, const float* w_ih_dev, const float* w_hh_dev,
                    const float* bias_ih_seq_dev, const float* bias_hh_seq_dev,
                    const float* gx_seq_dev, int steps, sd_gru** out);
-/* Optional, only when every gx_i == I: gate-interleaved copies that enable the fused FFMA2 step kernel
- * (h @ W_hh^T + gates in one launch).  Row c' = 96*blk + 32*g + u of the permuted tensors holds original row
- * g*H + 32*blk + u (g = gate r/z/n); w_hh_perm_dev is additionally K-major: [n_types, H, 3H].  bias_*_perm_dev: [N, 3H] = bias[type(n)] in the same order. */
 /* Three bf16 planes of W_hh ([3][n_types][3H][H], w = p0 + p1 + p2 exactly) for the tcgen05 recurrent product
  * h W_hh^T (recurrent.py:339) of the bf16x3 / bf16 precisions.  Optional: without it the FFMA kernels are used. */
 int  sd_gru_set_bf16x3(sd_gru* g, const uint16_t* w_hh_planes_dev);
 /* Two fp16 planes of W_hh ([2][n_types][3H][H], as sd_glin_set_f16x2) for the recurrent product under SD_PREC_F16X2 (recurrent.py:339). */
 int  sd_gru_set_f16x2(sd_gru* g, const uint16_t* w_hh_f16_dev);
+/* Optional, only when every gx_i == I: gate-interleaved copies that enable the fused step kernels
+ * (h @ W_hh^T + gates in one launch, recurrent.py:339-358).  Row c' = 96*blk + 32*g + u of the permuted tensors holds original row
+ * g*H + 32*blk + u (g = gate r/z/n); w_hh_perm_dev is additionally K-major: [n_types, H, 3H].  bias_*_perm_dev: [N, 3H] = bias[type(n)] in the same order. */
 int  sd_gru_set_fused(sd_gru* g, const float* w_ih_perm_dev, const float* w_hh_perm_dev,
                       const float* bias_ih_perm_dev, const float* bias_hh_perm_dev);
+/* After sd_gru_set_fused: two fp16 planes ([2][n_types][3H][H], as sd_gru_set_f16x2) of W_hh with its ROWS in the gate-interleaved
+ * order.  Enables the fused tensor-core step under SD_PREC_F16X2: recurrent product on tcgen05 with the gates (recurrent.py:351-358)
+ * in its epilogue; the [B, N, 3H] product never reaches HBM. */
+int  sd_gru_set_fused_f16x2(sd_gru* g, const uint16_t* w_hh_perm_f16_dev);
 void sd_gru_destroy(sd_gru* g);
 size_t sd_encode_workspace_bytes(int windows, int obs_len, int num_nodes, int hidden, int layers);
 /* obs_dev [W, T, N, F] -> z_dev [W, N, latent] = final_act(fc(h_T)); final_act = SD_ACT_TANH_TANH for

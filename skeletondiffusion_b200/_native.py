@@ -85,6 +85,7 @@ SIGNATURES = {
     "sd_mahalanobis_loss_backward": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "sd_gru_create": (_I, [_I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, C.POINTER(_P)]),
     "sd_gru_set_fused": (_I, [_P, _P, _P, _P, _P]),
+    "sd_gru_set_fused_f16x2": (_I, [_P, _P]),
     "sd_gru_set_bf16x3": (_I, [_P, _P]),
     "sd_gru_set_f16x2": (_I, [_P, _P]),
     "sd_glin_set_f16x2": (_I, [_P, _P]),

@@ -614,7 +614,7 @@ int sd_gru_create(int num_nodes, const int32_t* node_types_host, int n_types, in
     }
     g->W_ih = w_ih_dev; g->W_hh = w_hh_dev; g->bias_ih_seq = bias_ih_seq_dev; g->bias_hh_seq = bias_hh_seq_dev; g->gx_seq = gx_seq_dev;
     g->W_ih_perm = g->W_hh_perm = g->bias_ih_perm = g->bias_hh_perm = nullptr;
-    g->W_hh_planes = nullptr; g->W_hh_f16 = nullptr; g->gx_host = nullptr;
+    g->W_hh_planes = nullptr; g->W_hh_f16 = nullptr; g->W_hh_perm_f16 = nullptr; g->gx_host = nullptr;
     if (gx_seq_dev) {   // host copy: the per-sample gate kernel takes gx_i by value (constant bank)
         const size_t n = (size_t)steps * num_nodes * num_nodes;
         g->gx_host = new (std::nothrow) float[n];
@@ -644,6 +644,13 @@ int sd_gru_set_fused(sd_gru* g, const float* w_ih_perm_dev, const float* w_hh_pe
     if (g->gx_seq) { set_error("sd_gru_set_fused: only for cells whose graph-influence sequence is the identity"); return SD_ERR_INVALID; }
     if (g->H % 32) { set_error("sd_gru_set_fused: hidden size must be a multiple of 32"); return SD_ERR_UNSUPPORTED; }
     g->W_ih_perm = w_ih_perm_dev; g->W_hh_perm = w_hh_perm_dev; g->bias_ih_perm = bias_ih_perm_dev; g->bias_hh_perm = bias_hh_perm_dev;
+    return SD_OK;
+}
+
+int sd_gru_set_fused_f16x2(sd_gru* g, const uint16_t* w_hh_perm_f16_dev) {
+    if (!g || !w_hh_perm_f16_dev) { set_error("sd_gru_set_fused_f16x2: null argument"); return SD_ERR_INVALID; }
+    if (!g->W_hh_perm) { set_error("sd_gru_set_fused_f16x2: call sd_gru_set_fused first (identity graph influence only)"); return SD_ERR_INVALID; }
+    g->W_hh_perm_f16 = w_hh_perm_f16_dev;
     return SD_OK;
 }
 
@@ -817,6 +824,32 @@ int sd_decode(const sd_glin* initial_hidden, const sd_gru* cell, const sd_glin* 
         const bool dense = cell->gx_seq != nullptr || fc->G != nullptr;
         const bool ok = (cell->gx_seq == nullptr || cell->gx_host) && (fc->G == nullptr || fc->G_host) && gru_head_supported(N, H, feat) &&
                         gru_sample_supported(N, H, hr, contiguous_view(xr_raw, N, 3 * H), hv, hw);
+        static int tcf_env = -1;       // SKELDIFF_GRU_TC_FUSED=0: recurrent product and gates as two kernels (A/B timing)
+        if (tcf_env < 0) { const char* e = getenv("SKELDIFF_GRU_TC_FUSED"); tcf_env = (e && e[0] == '0') ? 0 : 1; }
+        if (ok && tcf_env && !cell->gx_seq && cell->W_hh_perm_f16 && cell->W_ih_perm && cell->W_hh_planes && tc_split_planes() == 2 &&
+            precision == SD_PREC_BF16X3 && H % 32 == 0) {
+            // Identity graph influence on the two-plane tensor-core precision: ONE tcgen05 kernel per frame computes h W_hh^T (rows in the
+            // gate-interleaved order) and applies the gates in its epilogue (sd_glin_tc3.cu, T3_ACT_GRU).  Per frame it reads h (twice:
+            // operand and z h term, the second from L2), the loop-invariant x-side products and writes the new h: the [B, N, 3H] product
+            // (619 MB each way at B = 25 600) never exists.  The state ping-pongs between h and the (now unused) hr buffer.
+            rc = gru_product(cell->W_ih_perm, cell->IN, 3 * H, cell->types, N, make_view(*x_last), lat, contiguous_view_w(xr_raw, N, 3 * H), B, st);
+            if (rc) return rc;
+            sd_glin rec;
+            rec.N = N; rec.n_types = cell->n_types; rec.K = H; rec.OUT = 3 * H; rec.types = cell->types; rec.W = nullptr; rec.Wt = nullptr;
+            rec.bias_node = nullptr; rec.G = nullptr; rec.W_bf16 = cell->W_hh_planes; rec.planes = 3; rec.W_f16 = cell->W_hh_perm_f16; rec.G_host = nullptr;
+            float* h_cur = h;
+            float* h_nxt = hr;
+            for (int i = 0; i < ph; ++i) {
+                rc = glin_tc3_gru_step(&rec, contiguous_view(h_cur, N, H), contiguous_view(xr_raw, N, 3 * H), cell->bias_ih_perm, cell->bias_hh_perm,
+                                       contiguous_view_w(h_nxt, N, H), B, st);
+                if (rc) return rc;
+                ViewW o; o.ptr = out_dev + (size_t)i * N * feat; o.sb = (long long)ph * N * feat; o.sn = feat; o.rep = 1; o.width = feat;
+                rc = gru_head_fp32(fc->G, fc->W, fc->bias_node, fc->types, fc->n_types, N, H, feat, contiguous_view(h_nxt, N, H), o, SD_ACT_TANH, B, st);
+                if (rc) return rc;
+                float* t = h_cur; h_cur = h_nxt; h_nxt = t;
+            }
+            return SD_OK;
+        }
         if (ok && (dense || precision != SD_PREC_FP32)) {
             rc = gru_product(cell->W_ih, cell->IN, 3 * H, cell->types, N, make_view(*x_last), lat, contiguous_view_w(xr_raw, N, 3 * H), B, st);
             if (rc) return rc;

@@ -41,7 +41,9 @@ constexpr int T3_THREADS = 512;     // 16 warps = 4 warpgroups of 128 registers 
                                     // the epilogue warpgroup grows to T3_REGS_EPI (setmaxnreg), which pays for a residual prefetch
                                     // T3_RES_AHEAD chunks deep (one chunk in flight left the 4 warps waiting on L2 latency)
 constexpr int T3_REGS_MISC = 80, T3_REGS_EPI = 176, T3_RES_AHEAD = 3;
-constexpr int T3_MAX_STAGES = 8, T3_MAX_WSLOTS = 4;
+constexpr int T3_MAX_STAGES = 8, T3_MAX_WSLOTS = 4, T3_MAX_RES_SLOTS = 4;
+// Internal epilogue code (not an SD_ACT_* of the C ABI): fused GRU gates of the decoder's recurrent step, see the GRU block of the epilogue
+constexpr int T3_ACT_GRU = 3;
 constexpr int T3_PLANE_BYTES = T3_BM * 128;         // one plane tile: 128 rows x 128 B (64 k of 16-bit operands)
 // PL = 3: three bf16 planes (exact split, any fp32 magnitude), six products.  PL = 2: two fp16 planes, x = hi + lo * 2^-11 with
 // hi = fp16(x), lo = fp16((x - hi) * 2^11): 22 significand bits, three products (hi hi | hi lo + lo hi, the latter scaled by
@@ -60,6 +62,9 @@ struct T3Params {
     int out_tma;                // 1: the output chunk leaves through a TMA store of the warp's staging tile (two-plane kernel)
     int raw_slots;              // ATMA: fp32 activation k-blocks arrive by TMA in a ring of [128 rows][64 floats] boxes (warp 15)
     int stg2;                   // 1: two staging tiles per epilogue warp (a chunk's bulk store overlaps the next chunk)
+    int res_slots;              // boxes of the residual ring (2; the fused GRU step takes as many as fit, up to T3_MAX_RES_SLOTS)
+    const float* gru_bias_x;    // T3_ACT_GRU: gate-interleaved biases [N][3H] of the x side and of the h side
+    const float* gru_bias_h;
     NodeTypes types;
     const float* row_scale;
     const float* bias_node;
@@ -73,7 +78,7 @@ struct __align__(8) T3Barriers {
     uint64_t w_full, w_empty;
     uint64_t ws_full[T3_MAX_WSLOTS], ws_empty[T3_MAX_WSLOTS];       // weight slots (activation-stationary mode)
     uint64_t acc_full[2], acc_empty[2];
-    uint64_t res_full[2], res_empty[2];     // residual chunk ring (res_tma)
+    uint64_t res_full[T3_MAX_RES_SLOTS], res_empty[T3_MAX_RES_SLOTS];     // residual chunk ring (res_tma)
     uint64_t raw_full[4], raw_empty[4];     // fp32 activation ring (ATMA)
     uint32_t tmem_base, pad;
 };
@@ -137,7 +142,7 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
     float* epi_stage = epi_add + p.BN;                             // 4 warps x [32 rows][16 or 32 floats], swizzled
     float* res_buf = epi_stage + (p.stg2 ? 2 : 1) * 4 * 32 * t3_chunk_cols(PL);       // res_tma: 2 x [128 rows][32 floats]
     constexpr int RES_BOX = T3_BM * 32;
-    float* a_raw = res_buf + (RTMA ? 2 * RES_BOX : 0);             // ATMA: raw_slots x [128 rows][64 floats]
+    float* a_raw = res_buf + (RTMA ? p.res_slots * RES_BOX : 0);   // ATMA: raw_slots x [128 rows][64 floats]
     constexpr int RAW_BOX = T3_BM * T3_BK;
     T3Barriers* bars = reinterpret_cast<T3Barriers*>(a_raw + (ATMA ? p.raw_slots * RAW_BOX : 0));
 
@@ -149,7 +154,7 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
         mbar_init(&bars->w_empty, 1);
         for (int s = 0; s < T3_MAX_WSLOTS; ++s) { mbar_init(&bars->ws_full[s], 1); mbar_init(&bars->ws_empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&bars->acc_full[s], 1); mbar_init(&bars->acc_empty[s], 128); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&bars->res_full[s], 1); mbar_init(&bars->res_empty[s], 4); }
+        for (int s = 0; s < T3_MAX_RES_SLOTS; ++s) { mbar_init(&bars->res_full[s], 1); mbar_init(&bars->res_empty[s], 4); }
         for (int s = 0; s < 4; ++s) { mbar_init(&bars->raw_full[s], 1); mbar_init(&bars->raw_empty[s], 8); }
         fence_barrier_init();
     }
@@ -390,15 +395,20 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
         if (RTMA && lane == 0) {
             tma_prefetch_desc(&map_r);
             uint32_t slot = 0, ph = 0;
+            if (ACT == T3_ACT_GRU) tma_prefetch_desc(&map_a);
+            auto box = [&](const CUtensorMap* map, int col, int node, int row) {
+                mbar_wait(&bars->res_empty[slot], ph ^ 1u);
+                mbar_arrive_expect_tx(&bars->res_full[slot], (uint32_t)RES_BOX * 4u);
+                tma_load_3d(res_buf + (size_t)slot * RES_BOX, map, &bars->res_full[slot], col, node, row);
+                if (++slot == (uint32_t)p.res_slots) { slot = 0; ph ^= 1u; }
+            };
             for (long long it = item_lo; it < item_hi; ++it) {
                 const int node = (int)(it / p.MT), mt = (int)(it % p.MT);
-                for (int nt = nt_lo; nt < nt_hi; ++nt)
-                    for (int c0 = 0; c0 < p.BN; c0 += 32) {
-                        mbar_wait(&bars->res_empty[slot], ph ^ 1u);
-                        mbar_arrive_expect_tx(&bars->res_full[slot], (uint32_t)RES_BOX * 4u);
-                        tma_load_3d(res_buf + (size_t)slot * RES_BOX, &map_r, &bars->res_full[slot], nt * p.BN + c0, node, mt * T3_BM);
-                        if (++slot == 2) { slot = 0; ph ^= 1u; }
-                    }
+                for (int nt = nt_lo; nt < nt_hi; ++nt) {
+                    for (int c0 = 0; c0 < p.BN; c0 += 32) box(&map_r, nt * p.BN + c0, node, mt * T3_BM);
+                    // fused GRU step: after the three x-side gate boxes of the n-tile's 32 units, their previous hidden state
+                    if (ACT == T3_ACT_GRU) box(&map_a, nt * 32, node, mt * T3_BM);
+                }
             }
         }
         __syncwarp();
@@ -430,6 +440,11 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 for (int c = et; c < p.BN; c += 128) {
                     const int o = o0 + c;
+                    if (ACT == T3_ACT_GRU) {                    // gate biases of the n-tile's columns: h side / x side
+                        epi_mul[c] = __ldg(p.gru_bias_h + (long long)node * p.OUT + o);
+                        epi_add[c] = __ldg(p.gru_bias_x + (long long)node * p.OUT + o);
+                        continue;
+                    }
                     const float mul = p.ss ? (__ldg(p.ss + o) + 1.0f) : 1.0f;
                     const float bias = p.bias_node ? __ldg(p.bias_node + (long long)node * p.OUT + o) : 0.0f;
                     epi_mul[c] = mul;
@@ -476,6 +491,90 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
             const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 2u * (uint32_t)p.BN;
             const float* pre_base = p.pre.ptr ? p.pre.ptr + (long long)node * p.pre.sn + o0 + 4 * tcl : nullptr;
             constexpr float CS = PL == 3 ? 1.0f : 0.00048828125f;        // the lo planes carry a factor 2^11
+            if constexpr (ACT == T3_ACT_GRU && PL == 2) {
+                // ---------------------------------------------------------------- fused GRU step (recurrent.py:351-358), identity influence.
+                // The weight rows are gate-interleaved (sd_gru::W_hh_perm order): the 96 columns of n-tile nt are the r | z | n gate
+                // products of hidden units [32 nt, 32 nt + 32) of this node, so one n-tile's accumulators hold everything the new
+                // hidden state of those units needs.  The x-side products of the three gates (loop-invariant, same column order)
+                // and the previous hidden state arrive as four [128 samples][32 columns] boxes through the residual ring; the new
+                // state leaves as one bulk tensor store.  hr (619 MB per frame at B = 25 600) is neither written nor read back.
+                float4 gr[J], gz[J];
+#pragma unroll
+                for (int gch = 0; gch < 3; ++gch) {
+                    const int c0 = 32 * gch;
+                    if (gch == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the last store has read the tile
+                    __syncwarp();
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        uint32_t v[16], vc[16];
+                        tmem_ld_32x16(t_row + (uint32_t)(c0 + 16 * hf), v);
+                        tmem_ld_32x16(t_row + (uint32_t)(p.BN + c0 + 16 * hf), vc);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            float4 x;
+                            x.x = fmaf(__uint_as_float(vc[4 * q + 0]), CS, __uint_as_float(v[4 * q + 0]));
+                            x.y = fmaf(__uint_as_float(vc[4 * q + 1]), CS, __uint_as_float(v[4 * q + 1]));
+                            x.z = fmaf(__uint_as_float(vc[4 * q + 2]), CS, __uint_as_float(v[4 * q + 2]));
+                            x.w = fmaf(__uint_as_float(vc[4 * q + 3]), CS, __uint_as_float(v[4 * q + 3]));
+                            *reinterpret_cast<float4*>(stg + lane * 32 + 4 * ((4 * hf + q) ^ (lane & 7))) = x;
+                        }
+                    }
+                    __syncwarp();
+                    const float4 bh = *reinterpret_cast<const float4*>(epi_mul + c0 + 4 * tcl);
+                    const float4 bx = *reinterpret_cast<const float4*>(epi_add + c0 + 4 * tcl);
+                    mbar_wait(&bars->res_full[r_slot], r_phase);        // x-side product of this gate
+                    const float* xb = res_buf + (size_t)r_slot * RES_BOX + (quarter * 32 + tr) * 32 + 4 * tcl;
+                    float4 o[J];
+#pragma unroll
+                    for (int j = 0; j < J; ++j) {
+                        const int row = tr + RPI * j;
+                        float4 hx = *reinterpret_cast<const float4*>(stg + row * 32 + 4 * (tcl ^ (row & 7)));
+                        float4 xg = *reinterpret_cast<const float4*>(xb + RPI * j * 32);
+                        hx.x += bh.x; hx.y += bh.y; hx.z += bh.z; hx.w += bh.w;
+                        xg.x += bx.x; xg.y += bx.y; xg.z += bx.z; xg.w += bx.w;
+                        if (gch == 0) {
+                            gr[j].x = sigmoid_ex2(xg.x + hx.x); gr[j].y = sigmoid_ex2(xg.y + hx.y);
+                            gr[j].z = sigmoid_ex2(xg.z + hx.z); gr[j].w = sigmoid_ex2(xg.w + hx.w);
+                        } else if (gch == 1) {
+                            gz[j].x = sigmoid_ex2(xg.x + hx.x); gz[j].y = sigmoid_ex2(xg.y + hx.y);
+                            gz[j].z = sigmoid_ex2(xg.z + hx.z); gz[j].w = sigmoid_ex2(xg.w + hx.w);
+                        } else {
+                            o[j].x = tanh_ex2(fmaf(gr[j].x, hx.x, xg.x)); o[j].y = tanh_ex2(fmaf(gr[j].y, hx.y, xg.y));
+                            o[j].z = tanh_ex2(fmaf(gr[j].z, hx.z, xg.z)); o[j].w = tanh_ex2(fmaf(gr[j].w, hx.w, xg.w));
+                        }
+                    }
+                    fence_proxy_async();                            // the box reads are ordered before the copy engine's refill
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->res_empty[r_slot]);
+                    if (++r_slot == (uint32_t)p.res_slots) { r_slot = 0; r_phase ^= 1u; }
+                    if (gch == 2) {
+                        mbar_wait(&bars->res_full[r_slot], r_phase);    // previous hidden state of these units
+                        const float* hb = res_buf + (size_t)r_slot * RES_BOX + (quarter * 32 + tr) * 32 + 4 * tcl;
+#pragma unroll
+                        for (int j = 0; j < J; ++j) {
+                            const float4 hp = *reinterpret_cast<const float4*>(hb + RPI * j * 32);
+                            o[j].x = fmaf(gz[j].x, hp.x, fmaf(-o[j].x, gz[j].x, o[j].x));      // n - n z + z h
+                            o[j].y = fmaf(gz[j].y, hp.y, fmaf(-o[j].y, gz[j].y, o[j].y));
+                            o[j].z = fmaf(gz[j].z, hp.z, fmaf(-o[j].z, gz[j].z, o[j].z));
+                            o[j].w = fmaf(gz[j].w, hp.w, fmaf(-o[j].w, gz[j].w, o[j].w));
+                        }
+                        fence_proxy_async();
+                        __syncwarp();                               // every lane has read its transposed values and its box rows
+                        if (lane == 0) mbar_arrive(&bars->res_empty[r_slot]);
+                        if (++r_slot == (uint32_t)p.res_slots) { r_slot = 0; r_phase ^= 1u; }
+#pragma unroll
+                        for (int j = 0; j < J; ++j) *reinterpret_cast<float4*>(stg + (tr + RPI * j) * 32 + 4 * tcl) = o[j];
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                                         :: "l"(&map_o), "r"(smem_u32(stg)), "r"(nt * 32), "r"(node), "r"(mt * T3_BM + quarter * 32) : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                    }
+                }
+            } else
             for (int c0 = 0; c0 < p.BN; c0 += CW) {
                 float4 pp[J];                                   // partial product of the first K segment (K-split layers)
                 if (pre_base) {
@@ -542,7 +641,7 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                     fence_proxy_async();                        // the reads above are ordered before the copy engine's refill
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars->res_empty[r_slot]);
-                    if (++r_slot == 2) { r_slot = 0; r_phase ^= 1u; }
+                    if (++r_slot == (uint32_t)p.res_slots) { r_slot = 0; r_phase ^= 1u; }
                 }
                 if (HAS_RES && !res_tma) {                      // rotate the ring, fetch the chunk AHEAD positions ahead
 #pragma unroll
@@ -662,7 +761,11 @@ static int t3_launch_t(const CUtensorMap& mw, const CUtensorMap& mr, const CUten
 
 // out = epilogue(A @ W^T) with fp32 views; the caller guarantees G == identity for this call
 // one launch over the weight columns [k_base, k_base + K0 + K1) of the layer; `pre` (optional) is added before the epilogue
-static int t3_launch_one(const sd_glin* L, const GlinCall& c, const ViewW& out, bool apply_epilogue, int k_base, const View* pre, cudaStream_t st) {
+// gru (optional): fused GRU step.  L is W_hh in the gate-interleaved row order viewed as a graph-linear H -> 3H, c.a0 the previous
+// hidden state, `out` the NEW hidden state [B, N, H]; xr holds the x-side products in the same column order.
+struct T3Gru { View xr; const float* bias_x; const float* bias_h; };
+static int t3_launch_one(const sd_glin* L, const GlinCall& c, const ViewW& out, bool apply_epilogue, int k_base, const View* pre, cudaStream_t st,
+                         const T3Gru* gru = nullptr) {
     if (!L->W_bf16 || L->planes != 3) { set_error("bf16x3 path: 3-plane weights not set on this layer"); return SD_ERR_INVALID; }
     const int PL = (tl_split_planes == 2 && L->W_f16) ? 2 : 3;
     const int K0 = c.a0.width, K1 = c.a1.ptr ? c.a1.width : 0;
@@ -690,13 +793,29 @@ static int t3_launch_one(const sd_glin* L, const GlinCall& c, const ViewW& out, 
         if (as_env < 0) { const char* e = getenv("SKELDIFF_TC3_AS"); as_env = (e && e[0] == '0') ? 0 : 1; }
         const T3AsCfg as = as_env ? t3_as_cfg(Kuse, L->OUT, PL) : T3AsCfg{0, 0, 0};
         if (as.bn) { p.a_stationary = 1; p.BN = as.bn; p.NT = L->OUT / as.bn; p.nstage = as.nstage; p.wslots = as.wslots; }
+        if (gru) {      // one n-tile = the three gates of 32 hidden units: 96 columns, activation-stationary, whole K in the stage ring
+            if (PL != 2 || K1 != 0 || L->OUT != 3 * Kuse || Kuse % 32 || t3_kb(Kuse) > T3_MAX_STAGES || out.width != Kuse) {
+                set_error("fused GRU step: needs the two-plane split and a hidden size that is a multiple of 32 (H=%d, planes=%d)", Kuse, PL);
+                return SD_ERR_UNSUPPORTED;
+            }
+            p.a_stationary = 1; p.BN = 96; p.NT = L->OUT / 96; p.nstage = t3_kb(Kuse); p.wslots = 2;
+        }
     }
+    p.gru_bias_x = gru ? gru->bias_x : nullptr; p.gru_bias_h = gru ? gru->bias_h : nullptr;
+    p.res_slots = 2;
     p.tmem_cols = 4 * p.BN <= 32 ? 32 : (4 * p.BN <= 64 ? 64 : (4 * p.BN <= 128 ? 128 : (4 * p.BN <= 256 ? 256 : 512)));   // (main + corr) x 2 buffers
     p.types = L->types;
     p.out = out;
     int act = SD_ACT_NONE;
     bool has_res = false;
-    if (apply_epilogue) {
+    if (gru) {
+        p.row_scale = nullptr; p.bias_node = nullptr; p.ss = nullptr; p.residual = gru->xr; act = T3_ACT_GRU; has_res = true;
+        if (gru->xr.rep != 1 || c.a0.rep != 1 || out.rep != 1 || (reinterpret_cast<uintptr_t>(gru->xr.ptr) & 15u) || gru->xr.sb % 4 || gru->xr.sn % 4 ||
+            !gru->bias_x || !gru->bias_h || p.pre.ptr) {
+            set_error("fused GRU step: operands must be plain 16-byte aligned [B, N, *] tensors");
+            return SD_ERR_UNSUPPORTED;
+        }
+    } else if (apply_epilogue) {
         p.row_scale = c.row_scale; p.bias_node = c.epi.bias_node;
         p.ss = c.epi.ss ? c.epi.ss + (long long)c.epi.ss_row * c.epi.ss_stride : nullptr;
         p.residual = c.epi.residual; act = c.epi.act; has_res = c.epi.residual.ptr != nullptr;
@@ -729,7 +848,7 @@ static int t3_launch_one(const sd_glin* L, const GlinCall& c, const ViewW& out, 
         static int s2_env = -1;              // SKELDIFF_T3_STG2=0/1/2: never / wide outputs only (default) / whenever it fits
         if (s2_env < 0) { const char* e = getenv("SKELDIFF_T3_STG2"); s2_env = (e && e[0]) ? atoi(e) : 1; }
         const size_t extra = (size_t)4 * 32 * 32 * sizeof(float);
-        if (PL == 2 && s2_env && (s2_env == 2 || p.NT >= 4) && smem + extra <= (size_t)227 * 1024) { p.stg2 = 1; smem += extra; }
+        if (PL == 2 && !gru && s2_env && (s2_env == 2 || p.NT >= 4) && smem + extra <= (size_t)227 * 1024) { p.stg2 = 1; smem += extra; }
     }
     // Residual through a TMA ring (two-plane kernel): 32 KB of boxes [128 samples][32 columns] of the 3-D tensor (columns, node,
     // sample), loaded by the otherwise idle warp 14 two chunks ahead of the epilogue.  192 -> 192 + tanh + residual: 435 -> 312 us
@@ -743,7 +862,7 @@ static int t3_launch_one(const sd_glin* L, const GlinCall& c, const ViewW& out, 
         if (res_env < 0) { const char* e = getenv("SKELDIFF_T3_RES_TMA"); res_env = (e && e[0] == '0') ? 0 : 1; }
         const size_t ring = (size_t)2 * T3_BM * 32 * sizeof(float);
         static const int max_kb = t3_env("SKELDIFF_T3_RES_TMA_MAX_KB", 227);
-        if (res_env && has_res && PL == 2 && p.residual.rep == 1 && p.BN % 32 == 0 && smem + ring <= (size_t)max_kb * 1024) {
+        if ((res_env || gru) && has_res && PL == 2 && p.residual.rep == 1 && p.BN % 32 == 0 && smem + ring <= (size_t)max_kb * 1024) {
             cuuint64_t rdims[3] = {(cuuint64_t)L->OUT, (cuuint64_t)L->N, (cuuint64_t)c.B};
             cuuint64_t rstrides[2] = {(cuuint64_t)p.residual.sn * 4, (cuuint64_t)p.residual.sb * 4};
             cuuint32_t rbox[3] = {32, 1, (cuuint32_t)T3_BM};
@@ -751,16 +870,21 @@ static int t3_launch_one(const sd_glin* L, const GlinCall& c, const ViewW& out, 
             CUresult rr = enc(&mr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.residual.ptr), rdims, rstrides, rbox, restr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (rr == CUDA_SUCCESS) { p.res_tma = 1; smem += ring; }
+            if (rr == CUDA_SUCCESS && gru) {     // four boxes per n-tile (three gates + the previous state): a deeper ring while it fits
+                static const int want = t3_env("SKELDIFF_T3_GRU_SLOTS", 4);
+                while (p.res_slots < want && p.res_slots < T3_MAX_RES_SLOTS && smem + ring / 2 <= (size_t)227 * 1024) { ++p.res_slots; smem += ring / 2; }
+            }
         }
     }
+    if (gru && !p.res_tma) { set_error("fused GRU step: the operand ring does not fit / could not be mapped"); return SD_ERR_UNSUPPORTED; }
     // Output through TMA stores (two-plane kernel): the output is a 3-D tensor (columns, node, sample) like the residual.
     CUtensorMap mo = mw;
     p.out_tma = 0;
     {
         static int out_env = -1;             // SKELDIFF_T3_OUT_TMA=0: output by the epilogue's STG.128 (A/B timing)
         if (out_env < 0) { const char* e = getenv("SKELDIFF_T3_OUT_TMA"); out_env = (e && e[0] == '0') ? 0 : 1; }
-        if (out_env && PL == 2 && out.rep == 1 && p.BN % 32 == 0) {
-            cuuint64_t odims[3] = {(cuuint64_t)L->OUT, (cuuint64_t)L->N, (cuuint64_t)c.B};
+        if ((out_env || gru) && PL == 2 && out.rep == 1 && p.BN % 32 == 0) {
+            cuuint64_t odims[3] = {(cuuint64_t)(gru ? Kuse : L->OUT), (cuuint64_t)L->N, (cuuint64_t)c.B};
             cuuint64_t ostrides[2] = {(cuuint64_t)out.sn * 4, (cuuint64_t)out.sb * 4};
             cuuint32_t obox[3] = {32, 1, 32};
             cuuint32_t oestr[3] = {1, 1, 1};
@@ -769,6 +893,7 @@ static int t3_launch_one(const sd_glin* L, const GlinCall& c, const ViewW& out, 
             if (ro == CUDA_SUCCESS) p.out_tma = 1;
         }
     }
+    if (gru && !p.out_tma) { set_error("fused GRU step: the output tensor could not be mapped"); return SD_ERR_UNSUPPORTED; }
     // fp32 activations through a TMA ring (two-plane kernel without a residual, one K segment read in place): as many 32 KB
     // boxes as fit (2 .. 4); the producers then issue no global loads at all.
     CUtensorMap ma = mw;
@@ -779,7 +904,15 @@ static int t3_launch_one(const sd_glin* L, const GlinCall& c, const ViewW& out, 
         const size_t box = (size_t)T3_BM * T3_BK * sizeof(float);
         int slots = (int)(((size_t)227 * 1024 - smem) / box);
         if (slots > 4) slots = 4;
-        if (a_env && PL == 2 && !has_res && K1 == 0 && c.a0.rep == 1 && slots >= 2) {
+        if (gru) {          // the previous hidden state as [128 samples][32 units] boxes of the residual ring (not the k-block ring)
+            cuuint64_t adims[3] = {(cuuint64_t)K0, (cuuint64_t)L->N, (cuuint64_t)c.B};
+            cuuint64_t astrides[2] = {(cuuint64_t)c.a0.sn * 4, (cuuint64_t)c.a0.sb * 4};
+            cuuint32_t abox[3] = {32, 1, (cuuint32_t)T3_BM};
+            cuuint32_t aestr[3] = {1, 1, 1};
+            CUresult ra = enc(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(c.a0.ptr), adims, astrides, abox, aestr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (ra != CUDA_SUCCESS) { set_error("fused GRU step: cuTensorMapEncodeTiled (hidden state) failed: %d", (int)ra); return SD_ERR_CUDA; }
+        } else if (a_env && PL == 2 && !has_res && K1 == 0 && c.a0.rep == 1 && slots >= 2) {
             cuuint64_t adims[3] = {(cuuint64_t)K0, (cuuint64_t)L->N, (cuuint64_t)c.B};
             cuuint64_t astrides[2] = {(cuuint64_t)c.a0.sn * 4, (cuuint64_t)c.a0.sb * 4};
             cuuint32_t abox[3] = {(cuuint32_t)T3_BK, 1, (cuuint32_t)T3_BM};
@@ -794,6 +927,7 @@ static int t3_launch_one(const sd_glin* L, const GlinCall& c, const ViewW& out, 
     if (gangs < 1) gangs = 1;
     if (gangs > (long long)p.N * p.MT) gangs = (long long)p.N * p.MT;
     const int grid = (int)(p.a_stationary ? gangs : gangs * p.NT);
+    if (gru) return t3_launch_t<T3_ACT_GRU, true, 2, true, true, false>(mw, mr, mo, ma, p, grid, smem, st);
 #define T3_DISPATCH(PLN) \
     if (act == SD_ACT_NONE) return has_res ? t3_launch_t<SD_ACT_NONE, true, PLN>(mw, mr, mo, ma, p, grid, smem, st) : t3_launch_t<SD_ACT_NONE, false, PLN>(mw, mr, mo, ma, p, grid, smem, st); \
     if (act == SD_ACT_TANH) return has_res ? t3_launch_t<SD_ACT_TANH, true, PLN>(mw, mr, mo, ma, p, grid, smem, st) : t3_launch_t<SD_ACT_TANH, false, PLN>(mw, mr, mo, ma, p, grid, smem, st); \
@@ -824,6 +958,21 @@ int glin_tc3_launch(const sd_glin* L, const GlinCall& c, const ViewW& out, bool 
     GlinCall c2 = c; c2.a0 = c.a1; c2.a1.ptr = nullptr; c2.a1.width = 0;
     const View pre = contiguous_view(c.scratch, L->N, L->OUT);
     return t3_launch_one(L, c2, out, true, K0, &pre, st);
+}
+
+// One decoder / encoder GRU step with identity graph influence on the two-plane tensor-core path: h_out = GRU(xr, h_in) with
+// W_hh in the gate-interleaved order (L->W_f16: [2][types][3H][H] planes of the permuted rows), xr = x-side products in the same
+// column order, bias_x / bias_h: [N][3H] permuted.  h_out must not alias h_in.
+int glin_tc3_gru_step(const sd_glin* L, const View& h_in, const View& xr, const float* bias_x, const float* bias_h, const ViewW& h_out,
+                      int B, cudaStream_t st) {
+    if (h_in.ptr == h_out.ptr) { set_error("fused GRU step: the new hidden state must not alias the previous one"); return SD_ERR_INVALID; }
+    GlinCall c;
+    c.a0 = h_in; c.a1.ptr = nullptr; c.a1.sb = c.a1.sn = 0; c.a1.rep = 1; c.a1.width = 0;
+    c.row_scale = nullptr; c.out = h_out; c.scratch = nullptr; c.B = B;
+    c.epi.bias_node = nullptr; c.epi.ss = nullptr; c.epi.ss_row_idx = nullptr; c.epi.ss_row = 0; c.epi.ss_stride = 0; c.epi.act = SD_ACT_NONE;
+    c.epi.residual.ptr = nullptr; c.epi.residual.sb = c.epi.residual.sn = 0; c.epi.residual.rep = 1; c.epi.residual.width = 0; c.epi.OUT = L->OUT;
+    const T3Gru g{xr, bias_x, bias_h};
+    return t3_launch_one(L, c, h_out, false, 0, nullptr, st, &g);
 }
 
 }  // namespace sd

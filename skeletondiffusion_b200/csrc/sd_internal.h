@@ -33,6 +33,7 @@ struct sd_gru {
     const float* W_hh_perm;  // K-major: [n_types][H][3H]
     const float* bias_ih_perm;  // [N][3H]
     const float* bias_hh_perm;  // [N][3H]
+    const uint16_t* W_hh_perm_f16;   // [2][n_types][3H][H] fp16 planes of W_hh in the gate-interleaved ROW order (fused tensor-core step) or null
 };
 
 struct sd_diffusion {
@@ -121,6 +122,8 @@ int gru_out_fc_fp32(const float* Wfc, const float* bias_node, const NodeTypes& t
                     const ViewW& out, int act, int B, cudaStream_t st);
 bool glin_tc3_supported(int K0, int K1, int OUT);
 int glin_tc3_launch(const sd_glin* L, const GlinCall& c, const ViewW& out, bool apply_epilogue, cudaStream_t st);
+int glin_tc3_gru_step(const sd_glin* L, const View& h_in, const View& xr, const float* bias_x, const float* bias_h, const ViewW& h_out,
+                      int B, cudaStream_t st);      // fused recurrent product + gates (identity influence, two-plane split)
 bool glin_tc_supported(int K0, int K1, int OUT);
 int glin_tc_launch(const sd_glin* L, const TcCall& c, cudaStream_t st);
 int cast_concat_bf16(const View& a0, const View& a1, __nv_bfloat16* out, int B, int N, cudaStream_t st);

@@ -140,4 +140,9 @@ __device__ __forceinline__ float tanh_ex2(float x) {
     return copysignf(__fdividef(1.0f - t, 1.0f + t), x);
 }
 
+// logistic function through MUFU.EX2 + MUFU.RCP (the gates of the fused GRU step; same formula as gru_gates_kernel<FAST>)
+__device__ __forceinline__ float sigmoid_ex2(float x) {
+    return __fdividef(1.0f, 1.0f + exp2f(-1.4426950408889634f * x));
+}
+
 }}  // namespace sd::tc

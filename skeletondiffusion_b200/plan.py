@@ -332,6 +332,9 @@ class GruPlan:
             self.bias_hh_perm = b_hh[:, perm].contiguous()
             nv.check(nv.load().sd_gru_set_fused(self.handle, self.w_ih_perm.data_ptr(), self.w_hh_perm.data_ptr(),
                                                 self.bias_ih_perm.data_ptr(), self.bias_hh_perm.data_ptr()), "sd_gru_set_fused")
+            # the same row order as fp16 planes [2, types, 3H, H]: fused tensor-core step (product + gates in one tcgen05 kernel)
+            self.w_hh_perm_f16 = _f16x2_planes(self.w_hh[:, perm].contiguous())
+            nv.check(nv.load().sd_gru_set_fused_f16x2(self.handle, self.w_hh_perm_f16.data_ptr()), "sd_gru_set_fused_f16x2")
 
     def __del__(self):
         try:

@@ -142,6 +142,41 @@ def test_decode_dense_influence_vs_oracle(cuda_device, dataset, precision):
     assert G.rel_err(out2.cpu(), ref2) < FP32_TOL
 
 
+@pytest.mark.parametrize("dataset", ["amass", "h36m", "freeman"])
+@pytest.mark.parametrize("dense_head", [False, True])
+def test_decode_fused_tensor_core_step_vs_oracle(cuda_device, dataset, dense_head):
+    """Identity influence on the GRU cell under fp16x2: ONE tcgen05 kernel per frame (recurrent product with gate-interleaved
+    weight rows + gates in the epilogue, operands through the residual ring, new state by bulk tensor store).  407 rows =
+    three full 128-sample tiles and a ragged one per node; typed weights differ per node; the output head's own influence is
+    identity or dense.  Against the CPU oracle (recurrent.py:333-358) and, tighter, against the exact-fp32 path."""
+    import skeletondiffusion_b200 as sdb
+    from skeletondiffusion_b200.testing import synth_state_dict
+    spec = sdb.get_skeleton(dataset)
+    ae, _ = sdb.build_models(spec, "cpu")
+    sd = synth_state_dict(ae.state_dict(), seed=11, mode="perturbed", gain=2.5)
+    for k in list(sd):
+        if ".rnn." in k and k.endswith(".G"):
+            sd[k] = torch.eye(spec.num_nodes)
+        if ".rnn." in k and k.endswith(".G_add"):
+            sd[k] = torch.zeros(spec.num_nodes, spec.num_nodes)
+        if not dense_head and k.endswith(".G") and ".rnn." not in k:
+            sd[k] = torch.eye(spec.num_nodes)
+    ae.load_state_dict(sd)
+    g = torch.Generator().manual_seed(9)
+    W, S, ph = 11, 37, 12
+    obs = (torch.randn(W, spec.obs_length, spec.num_nodes, 3, generator=g) * 0.3).clamp(-1, 1)
+    lat = torch.tanh(torch.randn(W * S, spec.num_nodes, 96, generator=g))
+    ref = oc.decode(sd, G.dataset_cfg(spec), obs.repeat_interleave(S, 0), lat, ph)
+    ae = ae.to(cuda_device)
+    out = ae.decode(obs.to(cuda_device), lat.to(cuda_device), None, ph=ph, precision="fp16x2")
+    exact = ae.decode(obs.to(cuda_device), lat.to(cuda_device), None, ph=ph, precision="fp32")
+    assert torch.isfinite(out).all()
+    assert G.rel_err(out.cpu(), ref) < FP32_TOL
+    assert G.rel_err(out.cpu(), exact.cpu()) < 2e-5
+    again = ae.decode(obs.to(cuda_device), lat.to(cuda_device), None, ph=ph, precision="fp16x2")
+    assert torch.equal(out, again)
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3", "fp16x2"])
 def test_encode_dense_influence_vs_oracle(cuda_device, precision):
     import skeletondiffusion_b200 as sdb
