@@ -47,6 +47,22 @@ def main(rep):
             st = sorted(((s[6:], int(r[c[s]] or 0)) for s in stalls), key=lambda kv: -kv[1])[:2]
             n = int(r[c["# Samples"]] or 0)
             print(f"{100 * n / total:5.1f}%  {r[c['Source']].strip()[:70]:70s} {st}")
+    # per CUDA source line (needs -lineinfo and --import-source on): samples, executed warp instructions, dominant stall reasons
+    src = list(csv.reader(io.StringIO(ncu(rep, "--page", "source", "--csv", "--print-source", "cuda,sass"))))
+    heads = [i for i, r in enumerate(src) if r and r[0] == "Line No"]
+    for k, start in enumerate(heads):
+        h = src[start]
+        end = heads[k + 1] - 2 if k + 1 < len(heads) else len(src)
+        i_samp, i_inst = h.index("# Samples"), h.index("Instructions Executed")
+        stalls = [(i, n) for i, n in enumerate(h) if n.startswith("stall_") and "Not Issued" not in n]
+        lines = [r for r in src[start + 1:end] if len(r) == len(h) and r[0].strip().isdigit()]
+        total = sum(int(r[i_samp] or 0) for r in lines) or 1
+        name = src[start - 1][1][:100] if start > 0 and len(src[start - 1]) > 1 else ""
+        print(f"\n## hottest source lines, kernel {k}: {name}   ({total} samples)")
+        for r in sorted(lines, key=lambda r: -int(r[i_samp] or 0))[:45]:
+            n = int(r[i_samp] or 0)
+            st = sorted(((nm[6:], int(r[i] or 0)) for i, nm in stalls), key=lambda kv: -kv[1])[:2]
+            print(f"{100 * n / total:5.1f}%  L{r[0]:>4s} {int(r[i_inst] or 0):>10d} inst  {r[1].strip()[:90]:90s} {st}")
 
 
 if __name__ == "__main__":

@@ -62,6 +62,8 @@ struct T3Params {
     int out_tma;                // 1: the output chunk leaves through a TMA store of the warp's staging tile (two-plane kernel)
     int raw_slots;              // ATMA: fp32 activation k-blocks arrive by TMA in a ring of [128 rows][64 floats] boxes (warp 15)
     int stg2;                   // 1: two staging tiles per epilogue warp (a chunk's bulk store overlaps the next chunk)
+    int merge_ld;               // two-plane epilogue: the four TMEM loads of a chunk before one wait (t3_chunk32_to_stage)
+    int tab_cols;               // columns of the per-node epilogue tables in shared memory (multiple of 16)
     int res_slots;              // boxes of the residual ring (2; the fused GRU step takes as many as fit, up to T3_MAX_RES_SLOTS)
     const float* gru_bias_x;    // T3_ACT_GRU: gate-interleaved biases [N][3H] of the x side and of the h side
     const float* gru_bias_h;
@@ -125,6 +127,32 @@ template <bool FAST> __device__ __forceinline__ float t3_tanh(float x) { return 
 #else
 #define T3_LDA(p) __ldg(p)
 #endif
+// One 32-column chunk of the two-plane accumulators (main + corr * 2^-11, times the row scale) from TMEM into the warp's swizzled
+// staging tile, row = lane.  merge: all four 16-column loads are issued before ONE wait (64 registers in flight) instead of two
+// load / wait / store rounds: one TMEM round trip less on the epilogue warps' critical path.
+__device__ __forceinline__ void t3_chunk32_to_stage(uint32_t t_main, uint32_t t_corr, float* stg, int lane, float rs, bool merge) {
+    constexpr float CS = 0.00048828125f;
+    uint32_t v0[16], c0[16], v1[16], c1[16];
+    auto put = [&](const uint32_t (&v)[16], const uint32_t (&vc)[16], int hf) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float4 x;
+            x.x = fmaf(__uint_as_float(vc[4 * q + 0]), CS, __uint_as_float(v[4 * q + 0])) * rs;
+            x.y = fmaf(__uint_as_float(vc[4 * q + 1]), CS, __uint_as_float(v[4 * q + 1])) * rs;
+            x.z = fmaf(__uint_as_float(vc[4 * q + 2]), CS, __uint_as_float(v[4 * q + 2])) * rs;
+            x.w = fmaf(__uint_as_float(vc[4 * q + 3]), CS, __uint_as_float(v[4 * q + 3])) * rs;
+            *reinterpret_cast<float4*>(stg + lane * 32 + 4 * ((4 * hf + q) ^ (lane & 7))) = x;
+        }
+    };
+    tmem_ld_32x16(t_main, v0);
+    tmem_ld_32x16(t_corr, c0);
+    if (merge) { tmem_ld_32x16(t_main + 16u, v1); tmem_ld_32x16(t_corr + 16u, c1); }
+    tmem_ld_wait();
+    put(v0, c0, 0);
+    if (!merge) { tmem_ld_32x16(t_main + 16u, v1); tmem_ld_32x16(t_corr + 16u, c1); tmem_ld_wait(); }
+    put(v1, c1, 1);
+}
+
 template <int ACT, bool HAS_RES, bool FAST, int PL, bool RTMA, bool ATMA>
 __global__ void __launch_bounds__(T3_THREADS, 1)
 glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_o,
@@ -138,8 +166,8 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
     constexpr int STAGE_BYTES = t3_stage_bytes(PL);
     uint8_t* a_smem = w_smem + (size_t)PL * (p.a_stationary ? p.wslots : p.KB) * w_block;   // [stage][plane][128 x 128 B]
     float* epi_mul = reinterpret_cast<float*>(a_smem + (size_t)p.nstage * STAGE_BYTES);
-    float* epi_add = epi_mul + p.BN;
-    float* epi_stage = epi_add + p.BN;                             // 4 warps x [32 rows][16 or 32 floats], swizzled
+    float* epi_add = epi_mul + p.tab_cols;                         // tab_cols: the columns this CTA produces for one node (BN, or OUT when it loops over the n-tiles)
+    float* epi_stage = epi_add + p.tab_cols;                       // 4 warps x [32 rows][16 or 32 floats], swizzled
     float* res_buf = epi_stage + (p.stg2 ? 2 : 1) * 4 * 32 * t3_chunk_cols(PL);       // res_tma: 2 x [128 rows][32 floats]
     constexpr int RES_BOX = T3_BM * 32;
     float* a_raw = res_buf + (RTMA ? p.res_slots * RES_BOX : 0);   // ATMA: raw_slots x [128 rows][64 floats]
@@ -226,7 +254,7 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
         auto emit = [&](const float4 (&v)[8]) {
             if (e_left <= 0) return;
             --e_left;
-            mbar_wait(&bars->empty[stage], phase ^ 1);
+            MBAR_WAIT_AT(&bars->empty[stage], phase ^ 1);
             uint8_t* st = a_smem + (size_t)stage * STAGE_BYTES;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -259,7 +287,7 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
             uint32_t rs = 0, rph = 0;
             for (long long q = 0; q < q_end; ++q) {
                 float4 v[8];
-                mbar_wait(&bars->raw_full[rs], rph);
+                MBAR_WAIT_AT(&bars->raw_full[rs], rph);
                 const float* box = a_raw + (size_t)rs * RAW_BOX + col4 * 4;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(box + (row0 + 16 * i) * T3_BK);
@@ -291,20 +319,20 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                 const int node = (int)g;
                 if (!as_mode && g != cur_g) {
                     // the previous group's MMAs (w_empty phase w_loads-1) must have retired before the tile is overwritten
-                    if (w_loads > 0) mbar_wait(&bars->w_empty, (w_loads - 1) & 1u);
+                    if (w_loads > 0) MBAR_WAIT_AT(&bars->w_empty, (w_loads - 1) & 1u);
                     mbar_arrive_expect_tx(&bars->w_full, (uint32_t)PL * (uint32_t)p.KB * w_block);
                     for (int pl = 0; pl < PL; ++pl)
                         for (int kb = 0; kb < p.KB; ++kb)
                             tma_load_3d(w_smem + (size_t)(pl * p.KB + kb) * w_block, &map_w, &bars->w_full, p.k_base + kb * T3_BK, my_nt * p.BN,
                                         pl * p.n_types + p.types.t[node]);
-                    mbar_wait(&bars->w_full, w_loads & 1u);
+                    MBAR_WAIT_AT(&bars->w_full, w_loads & 1u);
                     ++w_loads;
                     cur_g = g;
                 }
                 const int stage0 = stage; const uint32_t phase0 = phase;
                 for (int nt = nt_lo; nt < nt_hi; ++nt) {
                     stage = stage0; phase = phase0;             // as_mode: every n-tile re-reads the same KB stages
-                    mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1);
+                    MBAR_WAIT_AT(&bars->acc_empty[acc], acc_phase ^ 1);
                     tc_fence_after();
                     // two accumulators per tile: x0 w0 alone in "main", the five 2^-8 .. 2^-16 pairs in "corr" (see header)
                     const uint32_t d_main = tmem_base + acc * 2u * (uint32_t)p.BN, d_corr = d_main + (uint32_t)p.BN;
@@ -312,12 +340,12 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                         const uint8_t* w_tile = w_smem;         // plane pw of this k-block at w_tile + pw * w_plane_stride
                         uint32_t w_plane_stride = (uint32_t)p.KB * w_block;
                         if (as_mode) {
-                            mbar_wait(&bars->ws_full[ws_slot], ws_phase);
+                            MBAR_WAIT_AT(&bars->ws_full[ws_slot], ws_phase);
                             w_tile = w_smem + (size_t)ws_slot * PL * w_block; w_plane_stride = w_block;
                         } else {
                             w_tile = w_smem + (size_t)kb * w_block;
                         }
-                        if (nt == nt_lo) mbar_wait(&bars->full[stage], phase);
+                        if (nt == nt_lo) MBAR_WAIT_AT(&bars->full[stage], phase);
                         tc_fence_after();
                         const uint32_t a_base = smem_u32(a_smem + (size_t)stage * STAGE_BYTES);
                         uint32_t first_main = (kb == 0) ? 1u : 0u, first_corr = first_main;
@@ -361,7 +389,7 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                 const int type = p.types.t[(int)(it / p.MT)];
                 for (int nt = 0; nt < p.NT; ++nt)
                     for (int kb = 0; kb < p.KB; ++kb) {
-                        mbar_wait(&bars->ws_empty[slot], ph ^ 1u);
+                        MBAR_WAIT_AT(&bars->ws_empty[slot], ph ^ 1u);
                         mbar_arrive_expect_tx(&bars->ws_full[slot], (uint32_t)PL * w_block);
                         for (int pl = 0; pl < PL; ++pl)
                             tma_load_3d(w_smem + (size_t)(slot * PL + pl) * w_block, &map_w, &bars->ws_full[slot], p.k_base + kb * T3_BK, nt * p.BN,
@@ -380,7 +408,7 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
             for (long long it = item_lo; it < item_hi; ++it) {
                 const int node = (int)(it / p.MT), mt = (int)(it % p.MT);
                 for (int kb = 0; kb < p.KB; ++kb) {
-                    mbar_wait(&bars->raw_empty[rs], rph ^ 1u);
+                    MBAR_WAIT_AT(&bars->raw_empty[rs], rph ^ 1u);
                     mbar_arrive_expect_tx(&bars->raw_full[rs], (uint32_t)RAW_BOX * 4u);
                     tma_load_3d(a_raw + (size_t)rs * RAW_BOX, &map_a, &bars->raw_full[rs], kb * T3_BK, node, mt * T3_BM);
                     if (++rs == (uint32_t)p.raw_slots) { rs = 0; rph ^= 1u; }
@@ -397,7 +425,7 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
             uint32_t slot = 0, ph = 0;
             if (ACT == T3_ACT_GRU) tma_prefetch_desc(&map_a);
             auto box = [&](const CUtensorMap* map, int col, int node, int row) {
-                mbar_wait(&bars->res_empty[slot], ph ^ 1u);
+                MBAR_WAIT_AT(&bars->res_empty[slot], ph ^ 1u);
                 mbar_arrive_expect_tx(&bars->res_full[slot], (uint32_t)RES_BOX * 4u);
                 tma_load_3d(res_buf + (size_t)slot * RES_BOX, map, &bars->res_full[slot], col, node, row);
                 if (++slot == (uint32_t)p.res_slots) { slot = 0; ph ^= 1u; }
@@ -429,17 +457,24 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
         uint32_t acc = 0, acc_phase = 0;
         uint32_t r_slot = 0, r_phase = 0;                          // residual chunk ring (res_tma)
         constexpr bool res_tma = RTMA;
-        long long cur_g = -1;
+        long long cur_key = -1;
+        // tables for every column this CTA produces for a node (always in the weight-resident schedule: one n-tile per CTA; in the
+        // activation-stationary one when the host sized them for OUT columns: two-plane kernel), else per (node, n-tile)
+        const bool tab_node = !as_mode || p.tab_cols >= p.NT * p.BN;
         for (long long it = item_lo; it < item_hi; ++it)
         for (int nt = nt_lo; nt < nt_hi; ++nt) {
-            const long long g = (it / p.MT) * p.NT + nt;          // (node, n-tile): the epilogue tables change with it
             const int mt = (int)(it % p.MT);
             const int node = (int)(it / p.MT);
             const int o0 = nt * p.BN;
-            if (g != cur_g) {
+            // The epilogue tables change with the NODE only (a CTA walks the m-tiles of a node back to back): refilling them per
+            // (node, n-tile) put two named barriers and a global-load latency in front of every n-tile of the activation-stationary
+            // schedule (18 % of the epilogue warps' samples in the round-2 source-level capture).
+            const long long key = tab_node ? node : (long long)node * p.NT + nt;
+            const int tab0 = tab_node ? nt_lo * p.BN : o0, tab_n = tab_node ? (nt_hi - nt_lo) * p.BN : p.BN;
+            if (key != cur_key) {
                 asm volatile("bar.sync 1, 128;" ::: "memory");
-                for (int c = et; c < p.BN; c += 128) {
-                    const int o = o0 + c;
+                for (int c = et; c < tab_n; c += 128) {
+                    const int o = tab0 + c;
                     if (ACT == T3_ACT_GRU) {                    // gate biases of the n-tile's columns: h side / x side
                         epi_mul[c] = __ldg(p.gru_bias_h + (long long)node * p.OUT + o);
                         epi_add[c] = __ldg(p.gru_bias_x + (long long)node * p.OUT + o);
@@ -451,7 +486,7 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                     epi_add[c] = fmaf(bias, mul, p.ss ? __ldg(p.ss + p.OUT + o) : 0.0f);
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
-                cur_g = g;
+                cur_key = key;
             }
             // TMEM hands each lane one ROW of the tile; stored that way every LDG/STG.128 of a warp would touch 32
             // different rows (32 LSU wavefronts per instruction: in the second ncu capture the residual alone cost 140 us).
@@ -486,7 +521,7 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                     prefetch_l2_bulk(p.residual.ptr + (long long)(p.residual.rep == 1 ? b2 : b2 / p.residual.rep) * p.residual.sb +
                                      (long long)node2 * p.residual.sn + o2, (uint32_t)p.BN * 4u);
             }
-            mbar_wait(&bars->acc_full[acc], acc_phase);
+            MBAR_WAIT_AT(&bars->acc_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 2u * (uint32_t)p.BN;
             const float* pre_base = p.pre.ptr ? p.pre.ptr + (long long)node * p.pre.sn + o0 + 4 * tcl : nullptr;
@@ -504,26 +539,11 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                     const int c0 = 32 * gch;
                     if (gch == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the last store has read the tile
                     __syncwarp();
-#pragma unroll
-                    for (int hf = 0; hf < 2; ++hf) {
-                        uint32_t v[16], vc[16];
-                        tmem_ld_32x16(t_row + (uint32_t)(c0 + 16 * hf), v);
-                        tmem_ld_32x16(t_row + (uint32_t)(p.BN + c0 + 16 * hf), vc);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            float4 x;
-                            x.x = fmaf(__uint_as_float(vc[4 * q + 0]), CS, __uint_as_float(v[4 * q + 0]));
-                            x.y = fmaf(__uint_as_float(vc[4 * q + 1]), CS, __uint_as_float(v[4 * q + 1]));
-                            x.z = fmaf(__uint_as_float(vc[4 * q + 2]), CS, __uint_as_float(v[4 * q + 2]));
-                            x.w = fmaf(__uint_as_float(vc[4 * q + 3]), CS, __uint_as_float(v[4 * q + 3]));
-                            *reinterpret_cast<float4*>(stg + lane * 32 + 4 * ((4 * hf + q) ^ (lane & 7))) = x;
-                        }
-                    }
+                    t3_chunk32_to_stage(t_row + (uint32_t)c0, t_row + (uint32_t)(p.BN + c0), stg, lane, 1.0f, p.merge_ld != 0);
                     __syncwarp();
-                    const float4 bh = *reinterpret_cast<const float4*>(epi_mul + c0 + 4 * tcl);
-                    const float4 bx = *reinterpret_cast<const float4*>(epi_add + c0 + 4 * tcl);
-                    mbar_wait(&bars->res_full[r_slot], r_phase);        // x-side product of this gate
+                    const float4 bh = *reinterpret_cast<const float4*>(epi_mul + (o0 - tab0) + c0 + 4 * tcl);
+                    const float4 bx = *reinterpret_cast<const float4*>(epi_add + (o0 - tab0) + c0 + 4 * tcl);
+                    MBAR_WAIT_AT(&bars->res_full[r_slot], r_phase);        // x-side product of this gate
                     const float* xb = res_buf + (size_t)r_slot * RES_BOX + (quarter * 32 + tr) * 32 + 4 * tcl;
                     float4 o[J];
 #pragma unroll
@@ -549,7 +569,7 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                     if (lane == 0) mbar_arrive(&bars->res_empty[r_slot]);
                     if (++r_slot == (uint32_t)p.res_slots) { r_slot = 0; r_phase ^= 1u; }
                     if (gch == 2) {
-                        mbar_wait(&bars->res_full[r_slot], r_phase);    // previous hidden state of these units
+                        MBAR_WAIT_AT(&bars->res_full[r_slot], r_phase);    // previous hidden state of these units
                         const float* hb = res_buf + (size_t)r_slot * RES_BOX + (quarter * 32 + tr) * 32 + 4 * tcl;
 #pragma unroll
                         for (int j = 0; j < J; ++j) {
@@ -592,6 +612,9 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                     }
                 }
                 __syncwarp();                                   // the previous chunk has been read out of the staging tile
+                if constexpr (PL == 2) {
+                    t3_chunk32_to_stage(t_row + (uint32_t)c0, t_row + (uint32_t)(p.BN + c0), stg, lane, rs, p.merge_ld != 0);
+                } else
 #pragma unroll
                 for (int hf = 0; hf < CW / 16; ++hf) {              // 16 columns at a time: v + vc stay within 32 registers
                     uint32_t v[16], vc[16];
@@ -612,8 +635,8 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                     }
                 }
                 __syncwarp();
-                const float4 m4 = *reinterpret_cast<const float4*>(epi_mul + c0 + 4 * tcl);
-                const float4 a4 = *reinterpret_cast<const float4*>(epi_add + c0 + 4 * tcl);
+                const float4 m4 = *reinterpret_cast<const float4*>(epi_mul + (o0 - tab0) + c0 + 4 * tcl);
+                const float4 a4 = *reinterpret_cast<const float4*>(epi_add + (o0 - tab0) + c0 + 4 * tcl);
                 float4 o[J];
 #pragma unroll
                 for (int j = 0; j < J; ++j) {
@@ -631,7 +654,7 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                     if (HAS_RES && !res_tma) { o[j].x += rr[0][j].x; o[j].y += rr[0][j].y; o[j].z += rr[0][j].z; o[j].w += rr[0][j].w; }
                 }
                 if (res_tma) {                                  // this chunk's residual box: rows of the warp's lane quarter
-                    mbar_wait(&bars->res_full[r_slot], r_phase);
+                    MBAR_WAIT_AT(&bars->res_full[r_slot], r_phase);
                     const float* rb = res_buf + (size_t)r_slot * RES_BOX + (quarter * 32 + tr) * 32 + 4 * tcl;
 #pragma unroll
                     for (int j = 0; j < J; ++j) {
@@ -694,7 +717,9 @@ typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static size_t t3_misc_smem(int bn, int pl) { return 2 * (size_t)bn * 4 + 4 * 32 * t3_chunk_cols(pl) * 4 + sizeof(T3Barriers) + 1024; }
+// tab_cols: columns of the two epilogue tables (the n-tile of a weight-resident CTA, the whole OUT of an activation-stationary one)
+static int t3_tab_cols(int cols) { return (cols + 15) & ~15; }
+static size_t t3_misc_smem(int tab_cols, int pl) { return 2 * (size_t)t3_tab_cols(tab_cols) * 4 + 4 * 32 * t3_chunk_cols(pl) * 4 + sizeof(T3Barriers) + 1024; }
 static int t3_kb(int K) { return (K + T3_BK - 1) / T3_BK; }      // the last k-block may be partly filled (zero planes)
 static size_t t3_fixed_smem(int K, int bn, int pl) { return (size_t)pl * t3_kb(K) * bn * 128 + t3_misc_smem(bn, pl); }
 static int t3_env(const char* name, int dflt) { const char* e = getenv(name); return e && e[0] ? atoi(e) : dflt; }
@@ -712,7 +737,7 @@ static T3AsCfg t3_as_cfg(int K, int OUT, int pl) {
     for (int bn : cands) {
         if (OUT % bn || OUT / bn < 2) continue;
         auto fits = [&](int stages, int slots) {
-            return (size_t)stages * t3_stage_bytes(pl) + (size_t)slots * pl * bn * 128 + t3_misc_smem(bn, pl) <= 227 * 1024;
+            return (size_t)stages * t3_stage_bytes(pl) + (size_t)slots * pl * bn * 128 + t3_misc_smem(pl == 2 ? OUT : bn, pl) <= 227 * 1024;
         };
         if (pl == 3) { if (kb <= T3_MAX_STAGES && fits(kb, 2)) return {bn, 2, kb}; continue; }
         for (int slots = want_slots > T3_MAX_WSLOTS ? T3_MAX_WSLOTS : want_slots; slots >= 2; --slots)
@@ -798,9 +823,12 @@ static int t3_launch_one(const sd_glin* L, const GlinCall& c, const ViewW& out, 
                 set_error("fused GRU step: needs the two-plane split and a hidden size that is a multiple of 32 (H=%d, planes=%d)", Kuse, PL);
                 return SD_ERR_UNSUPPORTED;
             }
-            p.a_stationary = 1; p.BN = 96; p.NT = L->OUT / 96; p.nstage = t3_kb(Kuse); p.wslots = 2;
+            static const int gx_stages = t3_env("SKELDIFF_T3_GRU_XSTAGES", 0), g_wslots = t3_env("SKELDIFF_T3_GRU_WSLOTS", 2);
+            p.a_stationary = 1; p.BN = 96; p.NT = L->OUT / 96; p.nstage = t3_kb(Kuse) + gx_stages; p.wslots = g_wslots < 2 ? 2 : (g_wslots > T3_MAX_WSLOTS ? T3_MAX_WSLOTS : g_wslots);
+            if (p.nstage > T3_MAX_STAGES) p.nstage = T3_MAX_STAGES;
         }
     }
+    { static const int m = t3_env("SKELDIFF_T3_MERGE_LD", 1); p.merge_ld = m; }
     p.gru_bias_x = gru ? gru->bias_x : nullptr; p.gru_bias_h = gru ? gru->bias_h : nullptr;
     p.res_slots = 2;
     p.tmem_cols = 4 * p.BN <= 32 ? 32 : (4 * p.BN <= 64 ? 64 : (4 * p.BN <= 128 ? 128 : (4 * p.BN <= 256 ? 256 : 512)));   // (main + corr) x 2 buffers
@@ -840,7 +868,9 @@ static int t3_launch_one(const sd_glin* L, const GlinCall& c, const ViewW& out, 
                      const_cast<uint16_t*>(PL == 3 ? L->W_bf16 : L->W_f16), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (weights x3) failed: %d", (int)r); return SD_ERR_CUDA; }
-    size_t smem = (p.a_stationary ? (size_t)p.wslots * PL * p.BN * 128 + t3_misc_smem(p.BN, PL) : t3_fixed_smem(Kuse, p.BN, PL)) + (size_t)p.nstage * t3_stage_bytes(PL);
+    // per-node tables (all OUT columns) in the two-plane activation-stationary schedule; the three-plane one has no shared memory to spare
+    p.tab_cols = t3_tab_cols(p.a_stationary && PL == 2 ? L->OUT : p.BN);
+    size_t smem = (p.a_stationary ? (size_t)p.wslots * PL * p.BN * 128 + t3_misc_smem(p.tab_cols, PL) : t3_fixed_smem(Kuse, p.BN, PL)) + (size_t)p.nstage * t3_stage_bytes(PL);
     // Two staging tiles per epilogue warp (two-plane kernel, output through bulk stores): the store of chunk c overlaps chunk
     // c + 1 instead of being waited for at its start.  16 KB; taken first on wide outputs (many chunks per activation tile).
     p.stg2 = 0;
@@ -871,7 +901,7 @@ static int t3_launch_one(const sd_glin* L, const GlinCall& c, const ViewW& out, 
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (rr == CUDA_SUCCESS) { p.res_tma = 1; smem += ring; }
             if (rr == CUDA_SUCCESS && gru) {     // four boxes per n-tile (three gates + the previous state): a deeper ring while it fits
-                static const int want = t3_env("SKELDIFF_T3_GRU_SLOTS", 4);
+                static const int want = t3_env("SKELDIFF_T3_GRU_SLOTS", 3);
                 while (p.res_slots < want && p.res_slots < T3_MAX_RES_SLOTS && smem + ring / 2 <= (size_t)227 * 1024) { ++p.res_slots; smem += ring / 2; }
             }
         }

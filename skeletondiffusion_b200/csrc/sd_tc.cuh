@@ -45,6 +45,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
     }
 }
 
+__device__ __forceinline__ void mbar_timeout(uint64_t* bar, uint32_t parity) {
+    printf("skeldiff: mbarrier wait timed out (block %d thread %d bar %p parity %u state %016llx)\n", blockIdx.x, threadIdx.x,
+           (void*)bar, parity, *reinterpret_cast<volatile unsigned long long*>(bar));
+    __trap();
+}
+// The same bounded wait expanded AT THE CALL SITE, so that a profiler's source view attributes the waiting time to the line of
+// the kernel that waits (every inlined mbar_wait shares the lines above).
+#define MBAR_WAIT_AT(bar_, parity_) do { \
+        uint64_t* _b = (bar_); const uint32_t _p = (parity_); uint32_t _ok, _spins = 0; \
+        do { \
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}" \
+                         : "=r"(_ok) : "r"(sd::tc::smem_u32(_b)), "r"(_p), "r"(0x989680u) : "memory"); \
+            if (!_ok && ++_spins > (1u << 24)) sd::tc::mbar_timeout(_b, _p); \
+        } while (!_ok); \
+    } while (0)
+
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void tma_prefetch_desc(const void* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
