@@ -179,10 +179,13 @@ constexpr int AB_GROUPS = 1;                         // warp groups (group g tak
 constexpr int AB_COPY_WARP = AB_GROUPS * AB_HEADS;
 constexpr int AB_THREADS = (AB_COPY_WARP + 1) * 32;  // compute warps + 1 copy warp
 
-// MIX variant: 8 attention warps + 8 mix warps + the copy warp = 17 warps at 120 registers (no spills).  A version with 20 warps
+// MIX variant: 8 attention warps + the mix warps + the copy warp.  First version: 8 mix warps, one column per thread and pass, scalar
+// FFMAs (17 warps).  A version with 20 warps
 // and a setmaxnreg hand-over (copy / idle group 24, mix 88, attention 152) passed every small test and died with an illegal
 // instruction at B = 25 600 (the same kernel without the three setmaxnreg instructions is correct); not pursued, it is not needed.
-constexpr int AB_MIX_WARP0 = AB_HEADS, AB_MIX_WARPS = 8, AB_MIX_COPY_WARP = 16, AB_THREADS_MIX = 17 * 32;
+// six mix warps: 192 threads x 4 columns = two FFMA2 column pairs per thread; 15 warps leave 128 registers per thread (17 warps: 96,
+// and the pairwise mix - 42 + 42 live values - spilled 1.4 KB)
+constexpr int AB_MIX_WARP0 = AB_HEADS, AB_MIX_WARPS = 6, AB_MIX_COPY_WARP = AB_MIX_WARP0 + AB_MIX_WARPS, AB_THREADS_MIX = (AB_MIX_COPY_WARP + 1) * 32;
 struct __align__(8) AbBarriers { uint64_t full[AB_STAGES], done[AB_STAGES], mixed[AB_STAGES]; };
 
 __device__ __forceinline__ void ab_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -247,17 +250,22 @@ node_attention_bulk_kernel(const float* __restrict__ qkv, float* __restrict__ ou
             const int stage = k % AB_STAGES;
             tc::mbar_wait(&bars->full[stage], (uint32_t)(k / AB_STAGES) & 1u, 100000 + k);
             float* slab = in_buf + stage * IN_FLOATS;
-            float rs[N];
             const long long b = (long long)blockIdx.x + (long long)k * gridDim.x;
+            const float* rsp = row_scale ? row_scale + b * N : nullptr;       // re-read per pass (L1 broadcast): no N registers held
+            constexpr int MT = AB_MIX_WARPS * 32;
+            static_assert(ROW == 4 * MT, "four columns per mix thread: two FFMA2 pairs");
+#pragma unroll 1
+            for (int pr = 0; pr < 2; ++pr) {   // columns (mt, mt + 192) and (mt + 384, mt + 576): 441 issue slots per 882 products
+                const int c0 = mt + 2 * pr * MT;
+                float in[N][2], acc[N][2];
 #pragma unroll
-            for (int m = 0; m < N; ++m) rs[m] = row_scale ? __ldg(row_scale + b * N + m) : 1.0f;
-            for (int c = mt; c < ROW; c += AB_MIX_WARPS * 32) {
-                float in[N][1], acc[N][1];
+                for (int m = 0; m < N; ++m) {
+                    const float r = rsp ? __ldg(rsp + m) : 1.0f;
+                    in[m][0] = slab[m * ROW + c0] * r; in[m][1] = slab[m * ROW + c0 + MT] * r;
+                }
+                mix_nodes<N, 2>(G, in, acc);
 #pragma unroll
-                for (int m = 0; m < N; ++m) in[m][0] = slab[m * ROW + c] * rs[m];
-                mix_nodes<N, 1>(G, in, acc);
-#pragma unroll
-                for (int n2 = 0; n2 < N; ++n2) slab[n2 * ROW + c] = acc[n2][0];
+                for (int n2 = 0; n2 < N; ++n2) { slab[n2 * ROW + c0] = acc[n2][0]; slab[n2 * ROW + c0 + MT] = acc[n2][1]; }
             }
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&bars->mixed[stage]);
