@@ -57,9 +57,11 @@ def main(rep):
         stalls = [(i, n) for i, n in enumerate(h) if n.startswith("stall_") and "Not Issued" not in n]
         lines = [r for r in src[start + 1:end] if len(r) == len(h) and r[0].strip().isdigit()]
         total = sum(int(r[i_samp] or 0) for r in lines) or 1
+        if total < 1000:                 # headers and helper files with a handful of samples
+            continue
         name = src[start - 1][1][:100] if start > 0 and len(src[start - 1]) > 1 else ""
         print(f"\n## hottest source lines, kernel {k}: {name}   ({total} samples)")
-        for r in sorted(lines, key=lambda r: -int(r[i_samp] or 0))[:45]:
+        for r in sorted(lines, key=lambda r: -int(r[i_samp] or 0))[:30]:
             n = int(r[i_samp] or 0)
             st = sorted(((nm[6:], int(r[i] or 0)) for i, nm in stalls), key=lambda kv: -kv[1])[:2]
             print(f"{100 * n / total:5.1f}%  L{r[0]:>4s} {int(r[i_inst] or 0):>10d} inst  {r[1].strip()[:90]:90s} {st}")

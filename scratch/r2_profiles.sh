@@ -14,6 +14,8 @@ if [ "$1" != "launches-only" ]; then
 cap r2_final_tc3 "glin_tc3" 4 python scratch/prof_kernels.py tc3,tc3raw,qkv,toout
 cap r2_final_step_attn "reverse_step|node_attention_bulk" 2 python scratch/prof_kernels.py step,attn
 cap r2_final_dense "node_attention_bulk|gru_sample|gru_head|sample_mix" 9 python scratch/prof_mix.py
+# fused GRU step of the decoder (identity influence, fp16x2): the 6th launch of a decode
+"$(dirname "$0")"/prof_gru.sh && cp gpurun_out/r2_gru_step.summary.txt gpurun_out/r2_final_gru_step.summary.txt
 fi
 export PROF_DENOISER=1
 cap r2_final_attn_mix "node_attention_bulk_kernel<21, 1>|node_attention_bulk_kernelILi21ELb1" 1 python scratch/prof_mix.py
