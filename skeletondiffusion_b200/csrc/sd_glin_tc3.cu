@@ -62,6 +62,8 @@ struct T3Params {
     int out_tma;                // 1: the output chunk leaves through a TMA store of the warp's staging tile (two-plane kernel)
     int raw_slots;              // ATMA: fp32 activation k-blocks arrive by TMA in a ring of [128 rows][64 floats] boxes (warp 15)
     int stg2;                   // 1: two staging tiles per epilogue warp (a chunk's bulk store overlaps the next chunk)
+    int direct;                 // two-plane kernel, bare layer (no bias / scale-shift / activation / residual / partial product): the staging
+                                // tile after the TMEM read IS the SWIZZLE_128B image of the output box and leaves as it is
     int merge_ld;               // two-plane epilogue: the four TMEM loads of a chunk before one wait (t3_chunk32_to_stage)
     int tab_cols;               // columns of the per-node epilogue tables in shared memory (multiple of 16)
     int res_slots;              // boxes of the residual ring (2; the fused GRU step takes as many as fit, up to T3_MAX_RES_SLOTS)
@@ -165,10 +167,12 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
     uint8_t* w_smem = smem;                                        // resident: [plane][kb][BN x 128 B]; streamed: [slot][plane][BN x 128 B]
     constexpr int STAGE_BYTES = t3_stage_bytes(PL);
     uint8_t* a_smem = w_smem + (size_t)PL * (p.a_stationary ? p.wslots : p.KB) * w_block;   // [stage][plane][128 x 128 B]
-    float* epi_mul = reinterpret_cast<float*>(a_smem + (size_t)p.nstage * STAGE_BYTES);
+    // staging tiles first: they follow the 1024-byte aligned plane stages, so every warp's [32 rows][128 bytes] tile is 1024-byte
+    // aligned (what a SWIZZLE_128B bulk tensor store of the tile expects, see p.direct)
+    float* epi_stage = reinterpret_cast<float*>(a_smem + (size_t)p.nstage * STAGE_BYTES);   // 4 warps x [32 rows][16 or 32 floats], swizzled (x2: stg2)
+    float* epi_mul = epi_stage + (p.stg2 ? 2 : 1) * 4 * 32 * t3_chunk_cols(PL);
     float* epi_add = epi_mul + p.tab_cols;                         // tab_cols: the columns this CTA produces for one node (BN, or OUT when it loops over the n-tiles)
-    float* epi_stage = epi_add + p.tab_cols;                       // 4 warps x [32 rows][16 or 32 floats], swizzled
-    float* res_buf = epi_stage + (p.stg2 ? 2 : 1) * 4 * 32 * t3_chunk_cols(PL);       // res_tma: 2 x [128 rows][32 floats]
+    float* res_buf = epi_add + p.tab_cols;                         // res_tma: res_slots x [128 rows][32 floats]
     constexpr int RES_BOX = T3_BM * 32;
     float* a_raw = res_buf + (RTMA ? p.res_slots * RES_BOX : 0);   // ATMA: raw_slots x [128 rows][64 floats]
     constexpr int RAW_BOX = T3_BM * T3_BK;
@@ -614,6 +618,19 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                 __syncwarp();                                   // the previous chunk has been read out of the staging tile
                 if constexpr (PL == 2) {
                     t3_chunk32_to_stage(t_row + (uint32_t)c0, t_row + (uint32_t)(p.BN + c0), stg, lane, rs, p.merge_ld != 0);
+                    if (p.direct) {
+                        // Bare layer (raw products of a layer with a dense graph influence, to_qkv, first half of a K-split): nothing
+                        // is left to do per column, and the tile just written - row = lane, 16-byte chunk q at position q ^ (row & 7),
+                        // 1024-byte aligned - is exactly what a SWIZZLE_128B bulk tensor store reads.  No transposition, no second pass.
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                                         :: "l"(&map_o), "r"(smem_u32(stg)), "r"(o0 + c0), "r"(node), "r"(mt * T3_BM + quarter * 32) : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                        continue;
+                    }
                 } else
 #pragma unroll
                 for (int hf = 0; hf < CW / 16; ++hf) {              // 16 columns at a time: v + vc stay within 32 registers
@@ -873,12 +890,19 @@ static int t3_launch_one(const sd_glin* L, const GlinCall& c, const ViewW& out, 
     size_t smem = (p.a_stationary ? (size_t)p.wslots * PL * p.BN * 128 + t3_misc_smem(p.tab_cols, PL) : t3_fixed_smem(Kuse, p.BN, PL)) + (size_t)p.nstage * t3_stage_bytes(PL);
     // Two staging tiles per epilogue warp (two-plane kernel, output through bulk stores): the store of chunk c overlaps chunk
     // c + 1 instead of being waited for at its start.  16 KB; taken first on wide outputs (many chunks per activation tile).
+    // Bare layer on the two-plane kernel: direct SWIZZLE_128B store of the staging tile (see the kernel).  SKELDIFF_T3_DIRECT=0: off.
+    static const int direct_env = t3_env("SKELDIFF_T3_DIRECT", 1);
+    const bool want_direct = direct_env && PL == 2 && !gru && act == SD_ACT_NONE && !has_res && !p.ss && !p.bias_node && !p.pre.ptr &&
+                             out.rep == 1 && p.BN % 32 == 0;
+    p.direct = 0;
     p.stg2 = 0;
     {
         static int s2_env = -1;              // SKELDIFF_T3_STG2=0/1/2: never / wide outputs only (default) / whenever it fits
         if (s2_env < 0) { const char* e = getenv("SKELDIFF_T3_STG2"); s2_env = (e && e[0]) ? atoi(e) : 1; }
         const size_t extra = (size_t)4 * 32 * 32 * sizeof(float);
-        if (PL == 2 && !gru && s2_env && (s2_env == 2 || p.NT >= 4) && smem + extra <= (size_t)227 * 1024) { p.stg2 = 1; smem += extra; }
+        // (a direct store overlaps the next chunk's TMEM read only with a second tile; not at the price of the activation ring's two boxes)
+        const bool direct_room = want_direct && smem + extra + (K1 == 0 && c.a0.rep == 1 ? 2 * (size_t)T3_BM * T3_BK * sizeof(float) : 0) <= (size_t)227 * 1024;
+        if (PL == 2 && !gru && s2_env && (s2_env == 2 || p.NT >= 4 || direct_room) && smem + extra <= (size_t)227 * 1024) { p.stg2 = 1; smem += extra; }
     }
     // Residual through a TMA ring (two-plane kernel): 32 KB of boxes [128 samples][32 columns] of the 3-D tensor (columns, node,
     // sample), loaded by the otherwise idle warp 14 two chunks ahead of the epilogue.  192 -> 192 + tanh + residual: 435 -> 312 us
@@ -913,14 +937,15 @@ static int t3_launch_one(const sd_glin* L, const GlinCall& c, const ViewW& out, 
     {
         static int out_env = -1;             // SKELDIFF_T3_OUT_TMA=0: output by the epilogue's STG.128 (A/B timing)
         if (out_env < 0) { const char* e = getenv("SKELDIFF_T3_OUT_TMA"); out_env = (e && e[0] == '0') ? 0 : 1; }
-        if ((out_env || gru) && PL == 2 && out.rep == 1 && p.BN % 32 == 0) {
+        if ((out_env || gru || want_direct) && PL == 2 && out.rep == 1 && p.BN % 32 == 0) {
             cuuint64_t odims[3] = {(cuuint64_t)(gru ? Kuse : L->OUT), (cuuint64_t)L->N, (cuuint64_t)c.B};
             cuuint64_t ostrides[2] = {(cuuint64_t)out.sn * 4, (cuuint64_t)out.sb * 4};
             cuuint32_t obox[3] = {32, 1, 32};
             cuuint32_t oestr[3] = {1, 1, 1};
             CUresult ro = enc(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, out.ptr, odims, ostrides, obox, oestr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (ro == CUDA_SUCCESS) p.out_tma = 1;
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, want_direct ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (ro == CUDA_SUCCESS) { p.out_tma = 1; p.direct = want_direct ? 1 : 0; }
         }
     }
     if (gru && !p.out_tma) { set_error("fused GRU step: the output tensor could not be mapped"); return SD_ERR_UNSUPPORTED; }
