@@ -335,6 +335,35 @@ def kernel_rooflines(dev, spec, diff, peaks, precision="fp16x2"):
     return rl
 
 
+def decoder_frame_roofline(dev, spec, ae, obs_dev, W, S, peaks, precision, dense):
+    """One decoder frame at the bench batch: (decode of 24 frames - decode of 4 frames) / 20, CUDA events on the launching stream.
+    Identity influence under fp16x2: the fused tcgen05 GRU step (recurrent product + gates, DESIGN.md 4.13) + the output head;
+    algorithmic bytes per (sample, node) row: h operand 96 + x-side gate products 288 + new h 96 (step) + h 96 + pose 3 (head) floats.
+    Dense influence: recurrent product + per-sample gate kernel + head: h 96 + hr 288 written + hr, xr 576 + h 96 read
+    + h 96 written + head 99."""
+    B, N = W * S, spec.num_nodes
+    lat = torch.tanh(torch.randn(B, N, 96, device=dev))
+    prec = "bf16x3" if precision == "bf16" else precision
+
+    def dec(frames):
+        return _timed_kernel(dev, lambda: ae.decode(obs_dev, lat, None, ph=frames, precision=prec), iters=3)
+
+    t = (dec(24) - dec(4)) / 20.0
+    floats = (96 + 288 + 96 + 96 + 3) if not dense and prec == "fp16x2" else (96 + 288 + 576 + 96 + 96 + 99)
+    by = 4.0 * floats * B * N
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    traffic = None
+    if not dense and prec == "fp16x2":      # the fused step + the head, from their ncu --set full captures (profiles/r2_final_*.summary.txt)
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("decoder_frame_identity_fp16x2")
+        except Exception:
+            pass
+    return {"kernel": ("glin_tc3_kernel<T3_ACT_GRU> (h W_hh^T on tcgen05 + GRU gates in the epilogue) + gru_head_tiled_kernel" if not dense and prec == "fp16x2"
+                       else "glin_tc3 recurrent product + gate kernel + gru_head_tiled_kernel") + ", one decoder frame, B=25600",
+            "bound": "hbm", "achieved": by / t / 1e9, "peak": hbm, "unit": "GB/s", "frac": by / t / 1e9 / hbm, "traffic": traffic, "ms": t * 1e3,
+            "bytes_per_row_frame": 4 * floats, "peak_source": "MEASURED_PEAKS.json" if peaks.get("_measured") else "fallback"}
+
+
 def run_ours(args):
     import skeletondiffusion_b200 as sdb
     from skeletondiffusion_b200 import _native as nv
@@ -473,6 +502,11 @@ def run_ours(args):
     motions = B * world * args.steps
     value, e2e = motions / t_res, motions / t_e2e
     rl = kernel_rooflines(dev, spec, diff, peaks, args.precision)
+    try:
+        if args.precision != "fp32":    # (exact fp32: the FFMA2 step kernel of round 1, DESIGN.md table in section 4)
+            rl["decoder_frame"] = decoder_frame_roofline(dev, spec, ae, obs_dev, W, S, peaks, args.precision, args.perturbed)
+    except Exception as e:          # a secondary line must not cost the bench line
+        rl["decoder_frame"] = {"error": str(e)[:200]}
     dominant = {"fp16x2": "glin_tc3", "bf16x3": "glin_tc3_bf16x3", "fp32": "glin_ffma2", "bf16": "glin_tc_bf16"}[args.precision]
     dtype = {"fp32": "f32 (FFMA2, exact)", "bf16": "bf16 (tcgen05; stated tolerance, tests/test_gpu_tc.py)",
              "bf16x3": "f32-grade: fp32 operands split into 3 bf16 planes on tcgen05, fp32 accumulate; <=1e-4 vs the reference (tests/test_gpu_tc.py)",
