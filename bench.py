@@ -5,7 +5,7 @@ nonisotropic reverse diffusion with the Denoiser -> decode), AMASS eval configur
 observations, reference-style random-init weights.
 
   python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun)
-  python bench.py --impl reference --gpus N ...            # the reference algorithm's CPU path (oracle port)
+  python bench.py --impl reference --gpus N ...            # the UNMODIFIED reference (oracle/_ref) on the host cores; oracle port if absent
 
 Rank 0 prints ONE JSON line (see README/DESIGN for the keys).
 """

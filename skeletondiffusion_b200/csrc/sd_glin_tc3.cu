@@ -1,25 +1,29 @@
-// StaticGraphLinear with fp32-grade products on the bf16 tensor cores ("bf16x3").
+// StaticGraphLinear with fp32-grade products on the 16-bit tensor cores: fp32 operands are split into planes on the way into
+// shared memory, the plane products are accumulated in fp32 in TMEM, activations stay fp32 in HBM.
 //
-// fp32 operands are split into three bf16 planes, x = x0 + x1 + x2 (8 mantissa bits each, exact), and
-//     x . w  ~=  x0 w0 + x0 w1 + x0 w2 + x1 w0 + x1 w1 + x2 w0        (terms below 2^-24 |x||w| dropped)
-// is accumulated in fp32 in TMEM: six tcgen05.mma.kind::f16 per K = 16 step.
-// The tensor core TRUNCATES when it adds a K = 16 partial sum to the accumulator (measured, scratch/acc_bias.py: with
-// all six pairs in one accumulator the result was 12.5 ulp short in magnitude at K = 192, 7x the rms error of an FFMA
-// chain).  So x0 w0 goes to a "main" accumulator (K/16 truncating adds) and the five small pairs to a second one whose
-// truncation error is 2^-8 of that; the epilogue adds the two with one round-to-nearest FADD.  Activations stay fp32 in
-// HBM (4 B/element, the whole non-GEMM pipeline of the fp32 path is reused unchanged); the split happens
-// on the way into shared memory:
-//   warps 0-7  transform producers: coalesced LDG.128 of the fp32 tile rows (any sd_view: in-place repeat,
-//              two K segments), split, STS.64 into three SWIZZLE_128B K-major plane tiles, fence.proxy.async
-//   warps 8-11 epilogue: tcgen05.ld (main + corr), row scale, bias, scale/shift, libdevice tanhf, fp32 residual, fp32 store;
-//              16-column chunks transposed through a swizzled staging tile so that global accesses are coalesced
+// PL = 3 ("bf16x3"): x = x0 + x1 + x2, three bf16 planes of 8 significand bits each (exact), and
+//     x . w  ~=  x0 w0 + x0 w1 + x0 w2 + x1 w0 + x1 w1 + x2 w0        (terms below 2^-24 |x||w| dropped):
+// six tcgen05.mma.kind::f16 per K = 16 step.  The tensor core TRUNCATES when it adds a K = 16 partial sum to the accumulator
+// (measured, scratch/acc_bias.py: with all six pairs in one accumulator the result was 12.5 ulp short in magnitude at K = 192,
+// 7x the rms error of an FFMA chain), so x0 w0 goes to a "main" accumulator and the five small pairs to a second one whose
+// truncation error is 2^-8 of that; the epilogue adds the two with one round-to-nearest FADD.
+// PL = 2 ("fp16x2", the default): x = hi + lo 2^-11 with hi = fp16(x), lo = fp16((x - hi) 2^11): 22 significand bits, three
+// products (hi hi -> main | hi lo + lo hi -> corr, scaled by 2^-11 in the epilogue), 32 KB stages.
+//
+// Warp roles (512 threads, one CTA per SM, persistent over (node, m-tile) items):
+//   warps 0-7  transform producers: fp32 activation granules (LDG.128 of any sd_view, or LDS from the TMA-fed fp32 ring "ATMA"),
+//              split, STS.64 into SWIZZLE_128B K-major plane tiles, fence.proxy.async, arrive on full[stage]
+//   warps 8-11 epilogue (setmaxnreg: 176 registers): tcgen05.ld (main + corr) -> swizzled staging tile (row = lane) -> transposed
+//              read (8 lanes cover 128 contiguous bytes of a row) -> row scale, bias, scale/shift, MUFU tanh, residual (own loads, or
+//              [128 x 32] boxes of the TMA residual ring "RTMA") -> row-major staging -> one bulk tensor store per warp and chunk.
+//              Bare layers store the first staging image directly (p.direct); T3_ACT_GRU applies the GRU gates.
 //   warp 12    TMEM allocator, MMA issue; in the weight-resident schedule also the TMA of the weight planes
-//   warp 13    activation-stationary schedule only: streams (n-tile, k-block) weight planes through a two-slot TMA ring
-// Two schedules (weight-resident / activation-stationary) and the K-split of two-segment layers are described at the
-// places they are chosen (glin_tc3_launch, t3_launch_one).  Roofline: 6 x 2*K*OUT FLOP per row at the bf16 rate is
-// 0.14 ms for the 192 -> 192 layer at B = 25 600, the three fp32 streams (in, residual, out) are 0.19 ms of HBM time:
-// HBM is the binding floor; measured 0.28 ms bare / 0.46 ms with tanh + residual, where the four epilogue warps are
-// the limiter (profiles/README.md).
+//   warp 13    activation-stationary schedule: streams (n-tile, k-block) weight planes through a two-slot TMA ring
+//   warp 14    residual / GRU operand ring (RTMA);   warp 15: fp32 activation ring (ATMA)
+// Two schedules (weight-resident / activation-stationary) and the K-split of two-segment layers are described at the places they
+// are chosen (glin_tc3_launch, t3_launch_one).  Roofline of the 192 -> 192 layer at B = 25 600: the three fp32 streams (in,
+// residual, out) are 0.19 ms of HBM time, 3 x 2*K*OUT FLOP per row at the 16-bit rate 0.07 ms: HBM is the binding floor; measured
+// 0.30 ms with tanh + residual, 0.21 ms bare (DESIGN.md section 4 table, 4.15 for what the source-level profiles showed).
 //
 // Reference semantics: GraphLinear.forward, src/core/network/layers/graph_structural.py:30-43.
 #include "sd_internal.h"

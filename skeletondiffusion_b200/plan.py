@@ -47,6 +47,18 @@ def _f16x2_planes(w: torch.Tensor) -> torch.Tensor:
     return torch.stack([hi, lo], 0).contiguous()
 
 
+def gate_interleave_perm(hidden: int, device=None) -> torch.Tensor:
+    """Row order of the fused GRU-step kernels: new row 96 blk + 32 g + u holds original row g H + 32 blk + u (g = gate r / z / n of
+    `weight_hh` / `weight_ih`, recurrent.py:333-349), so every 96-row block - one n-tile of the GEMM - carries the three gates of
+    hidden units [32 blk, 32 blk + 32)."""
+    if hidden % 32:
+        raise ValueError("gate-interleaved GRU weights need a hidden size that is a multiple of 32")
+    blk = torch.arange(hidden // 32, device=device).view(-1, 1, 1)
+    g = torch.arange(3, device=device).view(1, -1, 1)
+    u = torch.arange(32, device=device).view(1, 1, -1)
+    return (g * hidden + 32 * blk + u).reshape(-1)
+
+
 def _is_identity(g: torch.Tensor) -> bool:
     return bool(torch.equal(g, torch.eye(g.shape[0], device=g.device, dtype=g.dtype)))
 
@@ -322,10 +334,7 @@ class GruPlan:
         nv.check(nv.load().sd_gru_set_f16x2(self.handle, self.w_hh_f16.data_ptr()), "sd_gru_set_f16x2")
         if self.identity and H % 32 == 0:
             # gate-interleaved copies for the fused FFMA2 GRU step: every 96-row block = gates r|z|n of 32 units
-            blk = torch.arange(H // 32, device=dev).view(-1, 1, 1)
-            g = torch.arange(3, device=dev).view(1, -1, 1)
-            u = torch.arange(32, device=dev).view(1, 1, -1)
-            perm = (g * H + 32 * blk + u).reshape(-1)                       # new row -> original row
+            perm = gate_interleave_perm(H, dev)                             # new row -> original row
             self.w_ih_perm = self.w_ih[:, perm].contiguous()
             self.w_hh_perm = self.w_hh[:, perm].transpose(1, 2).contiguous()     # K-major [types, H, 3H]
             self.bias_ih_perm = b_ih[:, perm].contiguous()

@@ -189,3 +189,32 @@ def test_reference_checkpoint_files_load_unchanged(tmp_path):
     # the other direction: a checkpoint written from our modules loads into the reference's, strict
     torch.save({"model": diff.state_dict()}, diff_path)
     ref_diff.load_state_dict(sdb.load_model_checkpoint(diff_path)["model"], strict=True)
+
+
+def test_gate_interleaved_gru_rows_reproduce_the_cell():
+    """Host logic of the fused GRU-step kernels (sd_gru_set_fused / sd_gru_set_fused_f16x2): with the rows of weight_ih / weight_hh
+    and the biases permuted by gate_interleave_perm, every 96-column block of the products holds gates r | z | n of 32 hidden units,
+    and gating block by block gives the reference cell's new state (oracle gru_cell, recurrent.py:333-358).  CPU, float64."""
+    from oracle import skeldiff_oracle as oc
+    from skeletondiffusion_b200.plan import gate_interleave_perm
+    H, IN, N, B = 96, 7, 5, 4
+    g = torch.Generator().manual_seed(11)
+    sd = {"weight_ih": torch.randn(3 * H, IN, generator=g, dtype=torch.float64) * 0.3, "weight_hh": torch.randn(3 * H, H, generator=g, dtype=torch.float64) * 0.1,
+          "bias_ih": torch.randn(3 * H, generator=g, dtype=torch.float64) * 0.1, "bias_hh": torch.randn(3 * H, generator=g, dtype=torch.float64) * 0.1}
+    x = torch.randn(B, N, IN, generator=g, dtype=torch.float64)
+    h = torch.tanh(torch.randn(B, N, H, generator=g, dtype=torch.float64))
+    ref = oc.gru_cell(sd, "", x, h, torch.eye(N, dtype=torch.float64), None)
+    perm = gate_interleave_perm(H)
+    assert sorted(perm.tolist()) == list(range(3 * H))
+    xr = x @ sd["weight_ih"][perm].t() + sd["bias_ih"][perm]
+    hr = h @ sd["weight_hh"][perm].t() + sd["bias_hh"][perm]
+    out = torch.empty_like(h)
+    for blk in range(H // 32):
+        xg, hg = xr[..., 96 * blk:96 * blk + 96], hr[..., 96 * blk:96 * blk + 96]
+        r = torch.sigmoid(xg[..., :32] + hg[..., :32])
+        z = torch.sigmoid(xg[..., 32:64] + hg[..., 32:64])
+        n = torch.tanh(xg[..., 64:] + r * hg[..., 64:])
+        out[..., 32 * blk:32 * blk + 32] = n - n * z + z * h[..., 32 * blk:32 * blk + 32]
+    assert torch.allclose(out, ref, atol=1e-12, rtol=0)
+    with pytest.raises(ValueError):
+        gate_interleave_perm(100)
