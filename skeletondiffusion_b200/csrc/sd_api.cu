@@ -434,13 +434,28 @@ int sd_denoiser_forward(const sd_denoiser* d, const sd_view* x, const sd_view* x
         // ResnetBlock (attention.py:91-102)
         rc = call(d->slot[s0], contiguous_view(cur, N, C), null_view(), nullptr, i, SD_ACT_TANH, nullptr, h, C);
         if (rc) return rc;
-        rc = call(d->slot[s0 + 1], contiguous_view(h, N, C), null_view(), nullptr, -1, SD_ACT_TANH, cur, xb, C);
-        if (rc) return rc;
+        {   // block2 + residual; when an attention block follows, its RMSNorm row factors come out of this layer's epilogue if the
+            // kernel that runs it can provide them (GlinCall::norm_out), else from the separate pass below
+            GlinCall c;
+            c.a0 = contiguous_view(h, N, C); c.a1 = null_view(); c.row_scale = nullptr;
+            c.epi = no_epilogue(C);
+            c.epi.act = SD_ACT_TANH;
+            c.epi.residual = contiguous_view(cur, N, C);
+            c.out = contiguous_view_w(xb, N, C);
+            c.scratch = scratch; c.B = B;
+            c.norm_out = (i != n_pairs - 1) ? inv : nullptr;
+            (void)tc3_take_norm_written();
+            rc = run_glin(d->slot[s0 + 1], c, precision, st);
+            if (rc) return rc;
+        }
+        const bool norm_fused = tc3_take_norm_written();
         cur = xb;
         if (i != n_pairs - 1) {
             // Residual(PreNorm(Attention))  (attention.py:16-17, 44-46, 122-136)
-            rc = row_inv_norm_fp32(xb, inv, (long long)rows, C, st);
-            if (rc) return rc;
+            if (!norm_fused) {
+                rc = row_inv_norm_fp32(xb, inv, (long long)rows, C, st);
+                if (rc) return rc;
+            }
             const sd_glin* Lq = d->slot[s0 + 2];
             if (Lq && Lq->G != nullptr && Lq->G_host && !Lq->bias_node && node_attention_mix_supported(N, d->heads, d->dim_head, qkv, att)) {
                 // dense graph influence on to_qkv: the GEMM writes the RAW products and the attention kernel mixes the nodes

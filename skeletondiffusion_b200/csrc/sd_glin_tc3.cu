@@ -66,6 +66,8 @@ struct T3Params {
     int out_tma;                // 1: the output chunk leaves through a TMA store of the warp's staging tile (two-plane kernel)
     int raw_slots;              // ATMA: fp32 activation k-blocks arrive by TMA in a ring of [128 rows][64 floats] boxes (warp 15)
     int stg2;                   // 1: two staging tiles per epilogue warp (a chunk's bulk store overlaps the next chunk)
+    float* norm_out;            // RTMA variant, CTA covers whole rows: inv[b * N + node] = 1 / max(||out row||, 1e-12) (the RMSNorm factor of
+                                // the NEXT layer, layers/attention.py:36) from the values the epilogue holds anyway; null: not wanted
     int direct;                 // two-plane kernel, bare layer (no bias / scale-shift / activation / residual / partial product): the staging
                                 // tile after the TMEM read IS the SWIZZLE_128B image of the output box and leaves as it is
     int merge_ld;               // two-plane epilogue: the four TMEM loads of a chunk before one wait (t3_chunk32_to_stage)
@@ -465,6 +467,7 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
         uint32_t acc = 0, acc_phase = 0;
         uint32_t r_slot = 0, r_phase = 0;                          // residual chunk ring (res_tma)
         constexpr bool res_tma = RTMA;
+        float nss[J];                                              // norm_out: sum of squares of this thread's 4 columns of rows tr + RPI j
         long long cur_key = -1;
         // tables for every column this CTA produces for a node (always in the weight-resident schedule: one n-tile per CTA; in the
         // activation-stationary one when the host sized them for OUT columns: two-plane kernel), else per (node, n-tile)
@@ -474,6 +477,10 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
             const int mt = (int)(it % p.MT);
             const int node = (int)(it / p.MT);
             const int o0 = nt * p.BN;
+            if (RTMA && PL == 2 && nt == nt_lo) {
+#pragma unroll
+                for (int j = 0; j < J; ++j) nss[j] = 0.0f;
+            }
             // The epilogue tables change with the NODE only (a CTA walks the m-tiles of a node back to back): refilling them per
             // (node, n-tile) put two named barriers and a global-load latency in front of every n-tile of the activation-stationary
             // schedule (18 % of the epilogue warps' samples in the round-2 source-level capture).
@@ -681,6 +688,7 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                     for (int j = 0; j < J; ++j) {
                         const float4 r4 = *reinterpret_cast<const float4*>(rb + RPI * j * 32);
                         o[j].x += r4.x; o[j].y += r4.y; o[j].z += r4.z; o[j].w += r4.w;
+                        if (PL == 2 && p.norm_out) nss[j] = fmaf(o[j].x, o[j].x, fmaf(o[j].y, o[j].y, fmaf(o[j].z, o[j].z, fmaf(o[j].w, o[j].w, nss[j]))));
                     }
                     fence_proxy_async();                        // the reads above are ordered before the copy engine's refill
                     __syncwarp();
@@ -725,6 +733,18 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
             tc_fence_before();
             mbar_arrive(&bars->acc_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (RTMA && PL == 2 && ACT != T3_ACT_GRU && p.norm_out && nt == nt_hi - 1) {
+                // Row norms of the finished rows (the CTA has produced every column of them): the LPR lanes that share a row fold their
+                // partial sums, the first of them writes the factor.  Saves the separate 413 MB pass over the output (3.7 % of a step).
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    float v = nss[j];
+#pragma unroll
+                    for (int off = LPR / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                    const int bj = bT0 + RPI * j;
+                    if (tcl == 0 && bj < p.B) p.norm_out[(long long)bj * p.N + node] = 1.0f / fmaxf(sqrtf(v), 1e-12f);
+                }
+            }
         }
         if (PL == 2 && p.out_tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");    // shared memory outlives the stores
     }
@@ -787,6 +807,8 @@ bool glin_tc3_supported(int K0, int K1, int OUT) {
 
 // operand split of the fp32-grade tensor-core path for the calls of this thread: 3 = bf16 planes, 2 = fp16 planes
 // (set by the C entry points from the precision argument: SD_PREC_BF16X3 / SD_PREC_F16X2)
+static thread_local bool tl_norm_written = false;
+bool tc3_take_norm_written() { const bool w = tl_norm_written; tl_norm_written = false; return w; }
 static thread_local int tl_split_planes = 3;
 int tc_split_planes() { return tl_split_planes; }
 void set_tc_split_planes(int planes) { tl_split_planes = planes == 2 ? 2 : 3; }
@@ -850,6 +872,7 @@ static int t3_launch_one(const sd_glin* L, const GlinCall& c, const ViewW& out, 
         }
     }
     { static const int m = t3_env("SKELDIFF_T3_MERGE_LD", 1); p.merge_ld = m; }
+    p.norm_out = nullptr;
     p.gru_bias_x = gru ? gru->bias_x : nullptr; p.gru_bias_h = gru ? gru->bias_h : nullptr;
     p.res_slots = 2;
     p.tmem_cols = 4 * p.BN <= 32 ? 32 : (4 * p.BN <= 64 ? 64 : (4 * p.BN <= 128 ? 128 : (4 * p.BN <= 256 ? 256 : 512)));   // (main + corr) x 2 buffers
@@ -935,6 +958,17 @@ static int t3_launch_one(const sd_glin* L, const GlinCall& c, const ViewW& out, 
         }
     }
     if (gru && !p.res_tma) { set_error("fused GRU step: the operand ring does not fit / could not be mapped"); return SD_ERR_UNSUPPORTED; }
+    // Row norms of the output from the epilogue (GlinCall::norm_out): only where the residual-ring variant runs and the CTA covers
+    // whole rows (activation-stationary schedule, or a single n-tile); tl_norm_written tells the caller whether it still has to run
+    // the separate pass.  SKELDIFF_T3_NORM_FUSED=0: never.
+    {
+        static const int nf_env = t3_env("SKELDIFF_T3_NORM_FUSED", 1);
+        if (nf_env && c.norm_out && apply_epilogue && !gru && !pre && PL == 2 && p.res_tma && (p.a_stationary || p.NT == 1) && out.rep == 1 &&
+            out.sb == (long long)L->N * L->OUT && out.sn == L->OUT) {
+            p.norm_out = c.norm_out;
+            tl_norm_written = true;
+        }
+    }
     // Output through TMA stores (two-plane kernel): the output is a 3-D tensor (columns, node, sample) like the residual.
     CUtensorMap mo = mw;
     p.out_tma = 0;

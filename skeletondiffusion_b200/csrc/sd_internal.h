@@ -73,7 +73,10 @@ struct GlinCall {
     ViewW out;
     float* scratch;   // needed iff G != null
     int B;
+    float* norm_out = nullptr;   // optional request: inv[b * N + n] = 1 / max(||out[b, n, :]||, 1e-12) written by the producing kernel when it
+                                 // can (glin_tc3, two-plane residual-ring variant); tc3_take_norm_written() says whether it was
 };
+bool tc3_take_norm_written();    // true once after a glin_tc3 launch on this thread that honoured GlinCall::norm_out
 int glin_forward_fp32(const float* W, const float* Wt, int K, int OUT, const NodeTypes& types, int N,
                       const float* G, const GlinCall& c, cudaStream_t st);
 int node_mix_fp32(const float* G, int N, int OUT, const float* y, long long y_sb, const float* row_scale,
