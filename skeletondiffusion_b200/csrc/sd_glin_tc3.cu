@@ -161,7 +161,9 @@ __device__ __forceinline__ void t3_chunk32_to_stage(uint32_t t_main, uint32_t t_
     put(v1, c1, 1);
 }
 
-template <int ACT, bool HAS_RES, bool FAST, int PL, bool RTMA, bool ATMA>
+// NORM: the epilogue also folds the sum of squares of the finished rows into p.norm_out (its own instantiation: the eight extra
+// accumulators cost the tanh + residual kernel 9 % - 304 -> 333 us - and are paid only by the launches that want the factors)
+template <int ACT, bool HAS_RES, bool FAST, int PL, bool RTMA, bool ATMA, bool NORM = false>
 __global__ void __launch_bounds__(T3_THREADS, 1)
 glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_o,
                 const __grid_constant__ CUtensorMap map_a, const T3Params p) {
@@ -477,9 +479,11 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
             const int mt = (int)(it % p.MT);
             const int node = (int)(it / p.MT);
             const int o0 = nt * p.BN;
-            if (RTMA && PL == 2 && nt == nt_lo) {
+            if constexpr (NORM) {
+                if (nt == nt_lo) {
 #pragma unroll
-                for (int j = 0; j < J; ++j) nss[j] = 0.0f;
+                    for (int j = 0; j < J; ++j) nss[j] = 0.0f;
+                }
             }
             // The epilogue tables change with the NODE only (a CTA walks the m-tiles of a node back to back): refilling them per
             // (node, n-tile) put two named barriers and a global-load latency in front of every n-tile of the activation-stationary
@@ -688,7 +692,7 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                     for (int j = 0; j < J; ++j) {
                         const float4 r4 = *reinterpret_cast<const float4*>(rb + RPI * j * 32);
                         o[j].x += r4.x; o[j].y += r4.y; o[j].z += r4.z; o[j].w += r4.w;
-                        if (PL == 2 && p.norm_out) nss[j] = fmaf(o[j].x, o[j].x, fmaf(o[j].y, o[j].y, fmaf(o[j].z, o[j].z, fmaf(o[j].w, o[j].w, nss[j]))));
+                        if constexpr (NORM) nss[j] = fmaf(o[j].x, o[j].x, fmaf(o[j].y, o[j].y, fmaf(o[j].z, o[j].z, fmaf(o[j].w, o[j].w, nss[j]))));
                     }
                     fence_proxy_async();                        // the reads above are ordered before the copy engine's refill
                     __syncwarp();
@@ -733,7 +737,7 @@ glin_tc3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
             tc_fence_before();
             mbar_arrive(&bars->acc_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-            if (RTMA && PL == 2 && ACT != T3_ACT_GRU && p.norm_out && nt == nt_hi - 1) {
+            if constexpr (NORM) if (nt == nt_hi - 1) {
                 // Row norms of the finished rows (the CTA has produced every column of them): the LPR lanes that share a row fold their
                 // partial sums, the first of them writes the factor.  Saves the separate 413 MB pass over the output (3.7 % of a step).
 #pragma unroll
@@ -813,13 +817,17 @@ static thread_local int tl_split_planes = 3;
 int tc_split_planes() { return tl_split_planes; }
 void set_tc_split_planes(int planes) { tl_split_planes = planes == 2 ? 2 : 3; }
 
-template <int ACT, bool HAS_RES, int PL, bool FAST = false, bool RTMA = false, bool ATMA = false>
+template <int ACT, bool HAS_RES, int PL, bool FAST = false, bool RTMA = false, bool ATMA = false, bool NORM = false>
 static int t3_launch_t(const CUtensorMap& mw, const CUtensorMap& mr, const CUtensorMap& mo, const CUtensorMap& ma, const T3Params& p, int grid, size_t smem, cudaStream_t st) {
     // the libdevice epilogue is kept for the three-plane kernel only (SKELDIFF_ACCURATE_EPILOGUE=1)
-    if (ACT != SD_ACT_NONE && !FAST && (PL == 2 || fast_epilogue())) return t3_launch_t<ACT, HAS_RES, PL, ACT != SD_ACT_NONE, RTMA, ATMA>(mw, mr, mo, ma, p, grid, smem, st);
-    if (HAS_RES && PL == 2 && !RTMA && p.res_tma) return t3_launch_t<ACT, HAS_RES, PL, FAST, HAS_RES && PL == 2, ATMA>(mw, mr, mo, ma, p, grid, smem, st);
-    if (!HAS_RES && PL == 2 && !ATMA && p.raw_slots) return t3_launch_t<ACT, HAS_RES, PL, FAST, RTMA, !HAS_RES && PL == 2>(mw, mr, mo, ma, p, grid, smem, st);
-    auto kern = glin_tc3_kernel<ACT, HAS_RES, FAST, PL, RTMA, ATMA>;
+    if (ACT != SD_ACT_NONE && !FAST && (PL == 2 || fast_epilogue())) return t3_launch_t<ACT, HAS_RES, PL, ACT != SD_ACT_NONE, RTMA, ATMA, NORM>(mw, mr, mo, ma, p, grid, smem, st);
+    if (HAS_RES && PL == 2 && !RTMA && p.res_tma) return t3_launch_t<ACT, HAS_RES, PL, FAST, HAS_RES && PL == 2, ATMA, NORM>(mw, mr, mo, ma, p, grid, smem, st);
+    if (!HAS_RES && PL == 2 && !ATMA && p.raw_slots) return t3_launch_t<ACT, HAS_RES, PL, FAST, RTMA, !HAS_RES && PL == 2, NORM>(mw, mr, mo, ma, p, grid, smem, st);
+    // row norms from the epilogue: one extra instantiation, tanh + residual through the ring on the two-plane kernel (what t3_launch_one admits)
+    constexpr bool NORM_OK = ACT == SD_ACT_TANH && HAS_RES && PL == 2 && FAST && RTMA && !ATMA;
+    if (NORM_OK && !NORM && p.norm_out) return t3_launch_t<ACT, HAS_RES, PL, FAST, RTMA, ATMA, NORM_OK>(mw, mr, mo, ma, p, grid, smem, st);
+    if (!NORM && p.norm_out) { set_error("glin_tc3: row norms requested from a kernel variant that does not compute them"); return SD_ERR_INVALID; }
+    auto kern = glin_tc3_kernel<ACT, HAS_RES, FAST, PL, RTMA, ATMA, NORM>;
     static unsigned long long configured = 0;      // bit d: attribute set on device d (it is per device)
     if (int rc_attr = opt_in_smem(kern, (size_t)((227 * 1024)), configured)) return rc_attr;
     kern<<<grid, T3_THREADS, smem, st>>>(mw, mr, mo, ma, p);
@@ -963,7 +971,8 @@ static int t3_launch_one(const sd_glin* L, const GlinCall& c, const ViewW& out, 
     // the separate pass.  SKELDIFF_T3_NORM_FUSED=0: never.
     {
         static const int nf_env = t3_env("SKELDIFF_T3_NORM_FUSED", 1);
-        if (nf_env && c.norm_out && apply_epilogue && !gru && !pre && PL == 2 && p.res_tma && (p.a_stationary || p.NT == 1) && out.rep == 1 &&
+        if (nf_env && c.norm_out && apply_epilogue && !gru && !pre && PL == 2 && act == SD_ACT_TANH && has_res && p.res_tma &&
+            (p.a_stationary || p.NT == 1) && out.rep == 1 &&
             out.sb == (long long)L->N * L->OUT && out.sn == L->OUT) {
             p.norm_out = c.norm_out;
             tl_norm_written = true;
